@@ -1,0 +1,130 @@
+"""ctypes binding of libfishing_b200.so (the C ABI declared in include/fishing_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point is called without a CUDA
+device, an exception is raised.  `python __graft_entry__.py build` (or gym_fishing_b200.build.build()) compiles the
+library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfishing_b200.so")
+
+# enums (include/fishing_b200.h)
+V0, V1, V2, V4 = 0, 1, 2, 4
+KIND_OF_ID = {"fishing-v0": V0, "fishing-v1": V1, "fishing-v2": V2, "fishing-v4": V4}
+ACT_F64, ACT_F32, ACT_I32, ACT_I64 = 0, 1, 2, 3
+AUTO_RESET, FREEZE_DONE = 1, 2
+POLICY_ACTIONS, POLICY_ESCAPEMENT, POLICY_MSY = 0, 1, 2
+STREAM_STEP, STREAM_AUTORESET, STREAM_RESET = 0, 1, 2
+
+EXPORTS = (
+    "fishing_abi_version", "fishing_error_string", "fishing_launch_count", "fishing_reset", "fishing_step",
+    "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
+    "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
+    "fishing_host_free", "fishing_vec_soa", "fishing_population_draw",
+)
+
+
+class FishingParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_actions", C.c_int32), ("Tmax", C.c_int32), ("flags", C.c_uint32),
+                ("r", C.c_double), ("K", C.c_double), ("sigma", C.c_double), ("C", C.c_double), ("x0", C.c_double),
+                ("sigma_p", C.c_double), ("seed", C.c_uint64)]
+
+
+class FishingSoA(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("years", C.c_void_p), ("K_env", C.c_void_p), ("r_env", C.c_void_p)]
+
+
+class FishingRolloutArgs(C.Structure):
+    _fields_ = [("policy", C.c_int32), ("action_dtype", C.c_int32), ("T", C.c_int64), ("step0", C.c_uint64),
+                ("S", C.c_double), ("S_env", C.c_void_p), ("msy_q", C.c_double), ("actions", C.c_void_p),
+                ("noise", C.c_void_p), ("noise_id_div", C.c_int64), ("out_return", C.c_void_p),
+                ("out_done_step", C.c_void_p), ("trace_obs", C.c_void_p), ("trace_reward", C.c_void_p),
+                ("trace_done", C.c_void_p), ("trace_action", C.c_void_p)]
+
+
+class FishingError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().fishing_error_string(code)
+        super().__init__(f"{where}: error {code}: {msg.decode() if msg else '?'}")
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises ImportError with build instructions if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA engine is not built and gym_fishing_b200 has no CPU fallback. "
+            "Run `python __graft_entry__.py build` (needs nvcc).")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER(FishingParams)
+    L.fishing_abi_version.restype = C.c_int
+    L.fishing_abi_version.argtypes = []
+    L.fishing_error_string.restype = C.c_char_p
+    L.fishing_error_string.argtypes = [C.c_int]
+    L.fishing_launch_count.restype = u64
+    L.fishing_launch_count.argtypes = []
+    L.fishing_reset.restype = C.c_int
+    L.fishing_reset.argtypes = [P, i64, i64, u64, vp, vp, FishingSoA, vp, vp]
+    L.fishing_step.restype = C.c_int
+    L.fishing_step.argtypes = [P, i64, i64, u64, vp, i32, vp, vp, FishingSoA, vp, vp, vp, vp, vp, vp, vp]
+    L.fishing_noise_fill.restype = C.c_int
+    L.fishing_noise_fill.argtypes = [u64, i32, i64, i64, u64, i64, vp, vp]
+    L.fishing_rollout.restype = C.c_int
+    L.fishing_rollout.argtypes = [P, i64, i64, C.POINTER(FishingRolloutArgs), FishingSoA, vp]
+    L.fishing_reduce_scratch_bytes.restype = i64
+    L.fishing_reduce_scratch_bytes.argtypes = [i64, i64]
+    L.fishing_reduce_stats.restype = C.c_int
+    L.fishing_reduce_stats.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    L.fishing_bmsy.restype = C.c_int
+    L.fishing_bmsy.argtypes = [i32, dbl, dbl, dbl, i32, C.POINTER(dbl), C.POINTER(dbl)]
+    L.fishing_population_draw.restype = C.c_int
+    L.fishing_population_draw.argtypes = [P, i64, vp, i32, dbl, vp, vp]
+    L.fishing_vec_create.restype = C.c_int
+    L.fishing_vec_create.argtypes = [P, i64, i64, i32, C.POINTER(vp)]
+    L.fishing_vec_destroy.restype = C.c_int
+    L.fishing_vec_destroy.argtypes = [vp]
+    L.fishing_vec_reset.restype = C.c_int
+    L.fishing_vec_reset.argtypes = [vp, vp]
+    L.fishing_vec_step.restype = C.c_int
+    L.fishing_vec_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.fishing_host_alloc.restype = C.c_int
+    L.fishing_host_alloc.argtypes = [C.POINTER(vp), i64]
+    L.fishing_host_free.restype = C.c_int
+    L.fishing_host_free.argtypes = [vp]
+    L.fishing_vec_soa.restype = C.c_int
+    L.fishing_vec_soa.argtypes = [vp, C.POINTER(FishingSoA)]
+    if L.fishing_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.fishing_abi_version()} != 1; rebuild")
+    _lib = L
+    return L
+
+
+def check(code, where):
+    if code != 0:
+        raise FishingError(code, where)
+
+
+def make_params(kind, *, r=0.3, K=1.0, sigma=0.0, C_=0.5, x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1, seed=0,
+                flags=0):
+    return FishingParams(kind=int(kind), n_actions=int(n_actions), Tmax=int(Tmax), flags=int(flags), r=float(r),
+                         K=float(K), sigma=float(sigma), C=float(C_), x0=float(x0), sigma_p=float(sigma_p),
+                         seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("gym_fishing_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch

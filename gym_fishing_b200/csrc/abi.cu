@@ -1,0 +1,377 @@
+// extern "C" boundary of libfishing_b200.so (declared in include/fishing_b200.h): argument validation, dispatch to the
+// kernels, and the host-buffer front end (fishing_vec_*) with its chunked three-stream copy/compute pipeline.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/fishing_b200.h"
+#include "common.cuh"
+
+#include "kernel_args.cuh"
+
+namespace fishing {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+static bool kind_ok(int kind) { return kind == FISHING_V0 || kind == FISHING_V1 || kind == FISHING_V2 || kind == FISHING_V4; }
+
+static int act_size(int dt) {
+  switch (dt) {
+    case FISHING_ACT_F64: return 8;
+    case FISHING_ACT_F32: return 4;
+    case FISHING_ACT_I32: return 4;
+    case FISHING_ACT_I64: return 8;
+    default: return 0;
+  }
+}
+
+static bool act_matches_kind(int kind, int dt) {
+  const bool discrete = dt == FISHING_ACT_I32 || dt == FISHING_ACT_I64;
+  return (kind == FISHING_V0) == discrete;
+}
+
+// x0 / K - 1, or x0 un-normalised for fishing-v4 (fishing_model_error.py:44).  Host IEEE double arithmetic; this
+// translation unit is compiled without -ffast-math, and a division followed by a subtraction cannot be contracted.
+static double reset_state_value(const fishing_params* p) {
+  if (p->kind == FISHING_V4) return p->x0;
+  volatile double q = p->x0 / p->K;
+  return q - 1.0;
+}
+
+static int check_soa(const fishing_params* p, const fishing_soa& s) {
+  if (!s.state || !s.years) return FISHING_E_ARG;
+  if (p->kind == FISHING_V4 && (!s.K_env || !s.r_env)) return FISHING_E_ARG;
+  if (!aligned(s.state, 8) || !aligned(s.years, 4)) return FISHING_E_ALIGN;
+  if (p->kind == FISHING_V4 && (!aligned(s.K_env, 8) || !aligned(s.r_env, 8))) return FISHING_E_ALIGN;
+  return 0;
+}
+
+}  // namespace fishing
+
+using namespace fishing;
+
+extern "C" {
+
+int fishing_abi_version(void) { return FISHING_ABI_VERSION; }
+
+uint64_t fishing_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* fishing_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case FISHING_E_ARG: return "fishing: bad argument (NULL pointer, negative size or unknown enum)";
+    case FISHING_E_KIND: return "fishing: action dtype / policy not valid for this environment id";
+    case FISHING_E_ALIGN: return "fishing: pointer not aligned to its element size";
+    case FISHING_E_NODEVICE: return "fishing: no usable CUDA device";
+    case FISHING_E_STATE: return "fishing: handle not reset yet or already destroyed";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "fishing: unknown error";
+}
+
+int fishing_reset(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                  const double* reset_noise, fishing_soa soa, double* out_obs, void* stream) {
+  if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind)) return FISHING_E_ARG;
+  if (int e = check_soa(p, soa)) return e;
+  if (out_obs && !aligned(out_obs, 8)) return FISHING_E_ALIGN;
+  if (n == 0) return 0;
+  ResetArgs a;
+  a.n = n; a.env_id0 = env_id0; a.epoch = epoch; a.seed = p->seed;
+  a.s_reset = reset_state_value(p);
+  a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
+  a.per_env = p->kind == FISHING_V4;
+  a.mask = mask; a.reset_noise = reset_noise;
+  a.state = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env; a.out_obs = out_obs;
+  return (int)launch_reset(a, static_cast<cudaStream_t>(stream));
+}
+
+int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                 int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
+                 double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
+                 void* stream) {
+  if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind) || !action || !out_obs || !out_reward || !out_done)
+    return FISHING_E_ARG;
+  const int asz = act_size(action_dtype);
+  if (!asz) return FISHING_E_ARG;
+  if (!act_matches_kind(p->kind, action_dtype)) return FISHING_E_KIND;
+  if (int e = check_soa(p, soa)) return e;
+  if (!aligned(action, asz) || !aligned(out_obs, 8) || !aligned(out_reward, 8) || (noise && !aligned(noise, 8)) ||
+      (reset_noise && !aligned(reset_noise, 8)) || (out_terminal && !aligned(out_terminal, 8)) ||
+      (out_stock && !aligned(out_stock, 8)) || (out_harvest && !aligned(out_harvest, 8)))
+    return FISHING_E_ALIGN;
+  if (n == 0) return 0;
+  StepArgs a;
+  a.n = n; a.env_id0 = env_id0; a.step_idx = step_idx; a.seed = p->seed;
+  a.r = p->r; a.K = p->K; a.sigma = p->sigma; a.C = p->C;
+  a.s_reset = reset_state_value(p);
+  a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
+  a.n_actions = (double)p->n_actions;
+  a.Tmax = p->Tmax; a.flags = p->flags;
+  a.action = action; a.noise = noise; a.reset_noise = reset_noise;
+  a.state_in = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
+  a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
+  a.out_stock = out_stock; a.out_harvest = out_harvest;
+  // 16-byte vector path: every array that is accessed two-wide must be aligned to its pair size
+  bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
+             aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
+             (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
+             (!out_harvest || aligned(out_harvest, 16));
+  if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
+  return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
+}
+
+int fishing_noise_fill(uint64_t seed, int32_t noise_stream, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                       double* out, void* stream) {
+  if (n < 0 || T < 0 || env_id0 < 0 || !out || noise_stream < 0 || noise_stream > 2) return FISHING_E_ARG;
+  if (!aligned(out, 8)) return FISHING_E_ALIGN;
+  if (n == 0 || T == 0) return 0;
+  return (int)launch_noise_fill(seed, noise_stream, n, env_id0, step0, T, out, static_cast<cudaStream_t>(stream));
+}
+
+int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const fishing_rollout_args* r, fishing_soa soa,
+                    void* stream) {
+  if (!p || !r || n < 0 || env_id0 < 0 || !kind_ok(p->kind) || r->T < 0) return FISHING_E_ARG;
+  if (r->policy < FISHING_POLICY_ACTIONS || r->policy > FISHING_POLICY_MSY) return FISHING_E_ARG;
+  if (int e = check_soa(p, soa)) return e;
+  int asz = 8;
+  if (r->policy == FISHING_POLICY_ACTIONS) {
+    if (!r->actions) return FISHING_E_ARG;
+    asz = act_size(r->action_dtype);
+    if (!asz) return FISHING_E_ARG;
+    if (!act_matches_kind(p->kind, r->action_dtype)) return FISHING_E_KIND;
+  }
+  const int64_t m = r->noise_id_div > 1 ? r->noise_id_div : 1;
+  // the fused kernel owns environments in pairs
+  if (n % 2 != 0 || env_id0 % 2 != 0) return FISHING_E_ARG;
+  if (m > 1 && (n % (2 * m) != 0 || env_id0 % (2 * m) != 0)) return FISHING_E_ARG;
+  if (m == 1) {
+    const bool ok = aligned(soa.state, 16) && aligned(soa.years, 8) &&
+                    (p->kind != FISHING_V4 || (aligned(soa.K_env, 16) && aligned(soa.r_env, 16))) &&
+                    (!r->actions || aligned(r->actions, 2 * asz)) && (!r->noise || aligned(r->noise, 16)) &&
+                    (!r->S_env || aligned(r->S_env, 16)) && (!r->out_return || aligned(r->out_return, 16)) &&
+                    (!r->out_done_step || aligned(r->out_done_step, 8)) && (!r->trace_obs || aligned(r->trace_obs, 16)) &&
+                    (!r->trace_reward || aligned(r->trace_reward, 16)) && (!r->trace_done || aligned(r->trace_done, 2)) &&
+                    (!r->trace_action || aligned(r->trace_action, 16));
+    if (!ok) return FISHING_E_ALIGN;
+  }
+  if (n == 0) return 0;
+  RolloutArgs a;
+  a.n = n; a.env_id0 = env_id0; a.T = r->T; a.step0 = r->step0; a.seed = p->seed;
+  a.r = p->r; a.K = p->K; a.sigma = p->sigma; a.C = p->C;
+  a.s_reset = reset_state_value(p);
+  a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
+  a.n_actions = (double)p->n_actions;
+  a.Tmax = p->Tmax; a.flags = p->flags;
+  a.discrete = p->kind == FISHING_V0;
+  a.action_dtype = r->action_dtype;
+  a.S = r->S; a.msy_q = r->msy_q; a.S_env = r->S_env;
+  a.actions = r->actions; a.noise = r->noise; a.noise_id_div = m;
+  a.state = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
+  a.out_return = r->out_return; a.out_done_step = r->out_done_step;
+  a.trace_obs = r->trace_obs; a.trace_reward = r->trace_reward; a.trace_done = r->trace_done;
+  a.trace_action = r->trace_action;
+  return (int)launch_rollout(a, p->kind, r->policy, static_cast<cudaStream_t>(stream));
+}
+
+int64_t fishing_reduce_scratch_bytes(int64_t n, int64_t groups) {
+  if (n <= 0 || groups <= 0 || n % groups != 0) return 0;
+  return reduce_scratch_doubles(n, groups) * (int64_t)sizeof(double);
+}
+
+int fishing_reduce_stats(const double* ret, const int32_t* done_step, int64_t n, int64_t groups, void* scratch,
+                         double* out, void* stream) {
+  if (!ret || !scratch || !out || n <= 0 || groups <= 0 || n % groups != 0) return FISHING_E_ARG;
+  if (!aligned(ret, 8) || !aligned(scratch, 8) || !aligned(out, 8)) return FISHING_E_ALIGN;
+  return (int)launch_reduce(ret, done_step, n, groups, static_cast<double*>(scratch), out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int fishing_population_draw(const fishing_params* p, int64_t n, const void* x, int32_t is_f32, double z, void* out,
+                            void* stream) {
+  if (!p || !kind_ok(p->kind) || n < 0 || !x || !out) return FISHING_E_ARG;
+  if (!aligned(x, is_f32 ? 4 : 8) || !aligned(out, is_f32 ? 4 : 8)) return FISHING_E_ALIGN;
+  if (n == 0) return 0;
+  return (int)launch_growth(p->kind, n, x, is_f32 != 0, p->r, p->K, p->C, p->sigma, z, out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out) {
+  if (!kind_ok(kind) || !S_out) return FISHING_E_ARG;
+  double* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, 2 * sizeof(double));
+  if (e != cudaSuccess) return (int)e;
+  e = launch_bmsy(kind, r, K, C, K_is_f64 != 0 || kind == FISHING_V4, dev, nullptr);
+  double host[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) return (int)e;
+  *S_out = host[0];
+  if (msy_out) *msy_out = host[1];
+  return 0;
+}
+
+// ================================================================================================ host-buffer front end
+struct fishing_vec {
+  fishing_params p;
+  int64_t n, env_id0;
+  int device;
+  uint64_t step_idx, epoch;
+  bool was_reset;
+  fishing_soa soa;
+  // device staging for one step
+  void* d_action;      // n * 8
+  double* d_noise;     // n
+  double* d_obs;       // == soa.state (obs are written in place)
+  double* d_reward;
+  uint8_t* d_done;
+  double* d_terminal;
+  cudaStream_t streams[3];
+  cudaEvent_t ev[3];
+  int64_t chunk;       // environments per pipeline chunk (even)
+};
+
+static void vec_free(fishing_vec* v) {
+  if (!v) return;
+  cudaFree(v->soa.state); cudaFree(v->soa.years); cudaFree(v->soa.K_env); cudaFree(v->soa.r_env);
+  cudaFree(v->d_action); cudaFree(v->d_noise); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_terminal);
+  for (int i = 0; i < 3; ++i) {
+    if (v->streams[i]) cudaStreamDestroy(v->streams[i]);
+    if (v->ev[i]) cudaEventDestroy(v->ev[i]);
+  }
+  delete v;
+}
+
+int fishing_vec_create(const fishing_params* p, int64_t n, int64_t env_id0, int32_t device, fishing_vec** out) {
+  if (!p || !out || n <= 0 || env_id0 < 0 || !kind_ok(p->kind)) return FISHING_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FISHING_E_NODEVICE;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  fishing_vec* v = new (std::nothrow) fishing_vec();
+  if (!v) return FISHING_E_ARG;
+  std::memset(v, 0, sizeof(*v));
+  v->p = *p; v->n = n; v->env_id0 = env_id0; v->device = device;
+  const size_t nd = (size_t)n * sizeof(double);
+  bool ok = cudaMalloc(&v->soa.state, nd) == cudaSuccess && cudaMalloc(&v->soa.years, (size_t)n * 4) == cudaSuccess &&
+            cudaMalloc(&v->d_action, nd) == cudaSuccess && cudaMalloc(&v->d_noise, nd) == cudaSuccess &&
+            cudaMalloc(&v->d_reward, nd) == cudaSuccess && cudaMalloc(&v->d_done, (size_t)n) == cudaSuccess &&
+            cudaMalloc(&v->d_terminal, nd) == cudaSuccess;
+  if (ok && p->kind == FISHING_V4)
+    ok = cudaMalloc(&v->soa.K_env, nd) == cudaSuccess && cudaMalloc(&v->soa.r_env, nd) == cudaSuccess;
+  for (int i = 0; ok && i < 3; ++i)
+    ok = cudaStreamCreateWithFlags(&v->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&v->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    e = cudaGetLastError();
+    vec_free(v);
+    return e != cudaSuccess ? (int)e : (int)cudaErrorMemoryAllocation;
+  }
+  v->d_obs = v->soa.state;
+  cudaMemset(v->d_terminal, 0xFF, nd);  // NaN until an episode actually ends
+  // ~6 chunks in flight hide the first H2D / last D2H; chunks stay even and 16-byte aligned
+  int64_t chunk = (n + 5) / 6;
+  chunk = (chunk + 1023) / 1024 * 1024;
+  if (chunk > n) chunk = n;
+  v->chunk = chunk;
+  *out = v;
+  return 0;
+}
+
+int fishing_vec_destroy(fishing_vec* v) {
+  if (!v) return FISHING_E_ARG;
+  cudaSetDevice(v->device);
+  for (int i = 0; i < 3; ++i) cudaStreamSynchronize(v->streams[i]);
+  vec_free(v);
+  return 0;
+}
+
+int fishing_vec_soa(fishing_vec* v, fishing_soa* out) {
+  if (!v || !out) return FISHING_E_ARG;
+  *out = v->soa;
+  return 0;
+}
+
+int fishing_vec_reset(fishing_vec* v, double* obs_out) {
+  if (!v) return FISHING_E_ARG;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  cudaStream_t st = v->streams[0];
+  int rc = fishing_reset(&v->p, v->n, v->env_id0, v->epoch, nullptr, nullptr, v->soa, nullptr, st);
+  if (rc) return rc;
+  v->epoch += 1;
+  v->was_reset = true;
+  if (obs_out) {
+    e = cudaMemcpyAsync(obs_out, v->soa.state, (size_t)v->n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaStreamSynchronize(st);
+}
+
+int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, const double* noise, double* obs_out,
+                     double* reward_out, uint8_t* done_out, double* terminal_out) {
+  if (!v || !action || !obs_out || !reward_out || !done_out) return FISHING_E_ARG;
+  if (!v->was_reset) return FISHING_E_STATE;
+  const int asz = act_size(action_dtype);
+  if (!asz) return FISHING_E_ARG;
+  if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  int rc = 0;
+  int k = 0;
+  for (int64_t off = 0; off < v->n && rc == 0; off += v->chunk, ++k) {
+    const int64_t len = (v->n - off < v->chunk) ? v->n - off : v->chunk;
+    cudaStream_t st = v->streams[k % 3];
+    char* d_act = static_cast<char*>(v->d_action) + off * asz;
+    e = cudaMemcpyAsync(d_act, static_cast<const char*>(action) + off * asz, (size_t)len * asz, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && noise)
+      e = cudaMemcpyAsync(v->d_noise + off, noise + off, (size_t)len * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = (int)e; break; }
+    fishing_soa s = v->soa;
+    s.state += off; s.years += off;
+    if (s.K_env) { s.K_env += off; s.r_env += off; }
+    rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, noise ? v->d_noise + off : nullptr,
+                      nullptr, s, v->d_obs + off, v->d_reward + off, v->d_done + off,
+                      terminal_out ? v->d_terminal + off : nullptr, nullptr, nullptr, st);
+    if (rc) break;
+    e = cudaMemcpyAsync(obs_out + off, v->d_obs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(reward_out + off, v->d_reward + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(done_out + off, v->d_done + off, (size_t)len, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && terminal_out)
+      e = cudaMemcpyAsync(terminal_out + off, v->d_terminal + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e = cudaStreamSynchronize(v->streams[i]);
+    if (e != cudaSuccess && rc == 0) rc = (int)e;
+  }
+  v->step_idx += 1;
+  return rc;
+}
+
+int fishing_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return FISHING_E_ARG;
+  return (int)cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
+}
+
+int fishing_host_free(void* ptr) { return ptr ? (int)cudaFreeHost(ptr) : FISHING_E_ARG; }
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Per-environment arithmetic of gym_fishing's step(), one IEEE-754 binary64 rounding per reference operation, in
+// the reference's evaluation order.  Every add/sub/mul/div goes through the __d*_rn
+// intrinsics, which the compiler never contracts into FMA, so the result is bit-identical to numpy/CPython.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/fishing_b200.h"
+
+namespace fishing {
+
+enum Growth { LOGISTIC = 0, TIPPING = 1 };
+// how r and K reach the kernel: shared scalars with K == 1 (the default; x/K and x*K are exact no-ops and are
+// skipped), shared scalars with general K, or per-environment arrays (fishing-v4).
+enum ParamMode { P_KONE = 0, P_UNIFORM = 1, P_PERENV = 2 };
+
+// Python builtin min(a, b): b if b < a else a (a NaN b returns a).   base_fishing_env.py:117
+__device__ __forceinline__ double py_min(double a, double b) { return (b < a) ? b : a; }
+// Python builtin max(a, b): b if b > a else a.                        base_fishing_env.py:74,118; policies.py:29
+__device__ __forceinline__ double py_max(double a, double b) { return (b > a) ? b : a; }
+// np.maximum(a, 0.0): NaN propagates, -0.0 -> +0.0.                   base_fishing_env.py:125-132
+__device__ __forceinline__ double np_max0(double a) { return (a > 0.0 || a != a) ? a : 0.0; }
+// np.clip(a, lo, hi): NaN propagates.                                 base_fishing_env.py:143-145
+__device__ __forceinline__ double np_clip(double a, double lo, double hi) { return (a < lo) ? lo : ((a > hi) ? hi : a); }
+__device__ __forceinline__ float np_clipf(float a, float lo, float hi) { return (a < lo) ? lo : ((a > hi) ? hi : a); }
+
+// get_quota, base_fishing_env.py:135-147
+template <int PM>
+__device__ __forceinline__ double quota_f64(double a, double K) {
+  const double t = __dadd_rn(np_clip(a, -1.0, 1.0), 1.0);
+  return PM == P_KONE ? t : __dmul_rn(t, K);
+}
+// float32 Box action under numpy>=2 promotion: clip, +1 and (for a Python-number K) *K are float32 operations; with
+// an np.float64 K (fishing-v4) the product is float64.
+template <int PM>
+__device__ __forceinline__ double quota_f32(float a, double K) {
+  const float t = __fadd_rn(np_clipf(a, -1.0f, 1.0f), 1.0f);
+  if (PM == P_PERENV) return __dmul_rn((double)t, K);
+  if (PM == P_KONE) return (double)t;
+  return (double)__fmul_rn(t, (float)K);
+}
+template <int PM>
+__device__ __forceinline__ double quota_int(long long a, double n_actions, double K) {
+  const double t = __ddiv_rn((double)a, n_actions);
+  return PM == P_KONE ? t : __dmul_rn(t, K);
+}
+
+// get_action, base_fishing_env.py:149-156
+template <int PM>
+__device__ __forceinline__ double action_cts(double q, double K) {
+  return __dsub_rn(PM == P_KONE ? q : __ddiv_rn(q, K), 1.0);
+}
+template <int PM>
+__device__ __forceinline__ double action_discrete(double q, double n_actions, double K) {
+  const double t = __dmul_rn(q, n_actions);
+  return rint(PM == P_KONE ? t : __ddiv_rn(t, K));  // Python round(): half to even, not range checked
+}
+
+// population_draw: base_fishing_env.py:121-133 (logistic) / fishing_tipping_env.py:24-35 (tipping point)
+template <int GROWTH, int PM>
+__device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy) {
+  const double frac = PM == P_KONE ? x1 : __ddiv_rn(x1, K);
+  const double room = __dsub_rn(1.0, frac);
+  if (GROWTH == LOGISTIC) {
+    double t = __dadd_rn(x1, __dmul_rn(__dmul_rn(r, x1), room));
+    // sigma == 0 adds +-0.0, which cannot change the clipped result (see DESIGN.md "noise when sigma = 0")
+    if (noisy) t = __dadd_rn(t, __dmul_rn(__dmul_rn(x1, sigma), z));
+    return np_max0(t);
+  } else {
+    double e = __dmul_rn(__dmul_rn(r, room), __dsub_rn(x1, C));
+    if (noisy) e = __dadd_rn(e, __dmul_rn(__dmul_rn(x1, sigma), z));
+    return np_max0(__dmul_rn(x1, exp(e)));
+  }
+}
+
+struct StepOut {
+  double s2;      // next normalised state
+  double reward;  // max(harvest, 0)
+  bool dead;      // stock <= 0 after growth
+  double stock;   // fish_population after growth (x2), before the x/K - 1 round trip
+  double harvest; // min(x, quota); differs from reward only for a negative quota
+};
+
+// BaseFishingEnv.step body, base_fishing_env.py:60-81, for one environment given its quota.
+template <int GROWTH, int PM>
+__device__ __forceinline__ StepOut step_core(double s, double quota, double z, double r, double K, double C,
+                                             double sigma, bool noisy) {
+  double x = __dadd_rn(s, 1.0);                     // get_fish_population :158-160
+  if (PM != P_KONE) x = __dmul_rn(x, K);
+  const double h = py_min(x, quota);                // harvest_draw :117
+  const double x1 = py_max(__dsub_rn(x, h), 0.0);   // :118
+  const double x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
+  StepOut o;
+  o.s2 = __dsub_rn(PM == P_KONE ? x2 : __ddiv_rn(x2, K), 1.0);  // get_state :162-164
+  o.reward = py_max(h, 0.0);                        // :74
+  o.dead = x2 <= 0.0;                               // :78
+  o.stock = x2;
+  o.harvest = h;
+  return o;
+}
+
+// action element types and their 2-wide vector forms
+template <int ACT>
+struct ActT;
+template <>
+struct ActT<FISHING_ACT_F64> { using type = double; using vec2 = double2; };
+template <>
+struct ActT<FISHING_ACT_F32> { using type = float; using vec2 = float2; };
+template <>
+struct ActT<FISHING_ACT_I32> { using type = int32_t; using vec2 = int2; };
+template <>
+struct ActT<FISHING_ACT_I64> { using type = long long; using vec2 = longlong2; };
+
+template <int PM, int ACT>
+__device__ __forceinline__ double quota_of(typename ActT<ACT>::type a, double n_actions, double K) {
+  if constexpr (ACT == FISHING_ACT_F64) return quota_f64<PM>(a, K);
+  else if constexpr (ACT == FISHING_ACT_F32) return quota_f32<PM>(a, K);
+  else return quota_int<PM>((long long)a, n_actions, K);
+}
+
+// fishing_model_error.py:37-38 / :42-43: K = clip(K_mean + sigma_p*zK, 0, 1e6); r likewise (K first).
+__device__ __forceinline__ double v4_param(double mean, double sigma_p, double z) {
+  return np_clip(__dadd_rn(mean, __dmul_rn(sigma_p, z)), 0.0, 1e6);
+}
+
+}  // namespace fishing

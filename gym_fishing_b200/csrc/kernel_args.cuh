@@ -1,0 +1,85 @@
+// Kernel argument blocks and launcher prototypes shared by step_kernels.cu, rollout_kernels.cu and abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fishing {
+
+struct StepArgs {
+  int64_t n;          // environments in this launch
+  int64_t env_id0;    // global id of element 0 (keys the Philox stream)
+  uint64_t step_idx;  // global lock-step counter t
+  uint64_t seed;
+  double r, K, sigma, C;
+  double s_reset;     // x0 / K - 1 (x0 itself for v4), precomputed on the host with the same IEEE operations
+  double K_mean, r_mean, sigma_p;
+  double n_actions;
+  int32_t Tmax;
+  uint32_t flags;
+  const void* __restrict__ action;
+  const double* __restrict__ noise;
+  const double* __restrict__ reset_noise;
+  const double* state_in;
+  int32_t* years;
+  double* K_env;
+  double* r_env;
+  double* out_obs;
+  double* __restrict__ out_reward;
+  uint8_t* __restrict__ out_done;
+  double* __restrict__ out_terminal;
+  double* __restrict__ out_stock;    // optional: fish_population after growth
+  double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
+};
+
+struct ResetArgs {
+  int64_t n, env_id0;
+  uint64_t epoch, seed;
+  double s_reset, K_mean, r_mean, sigma_p;
+  int32_t per_env;
+  const uint8_t* __restrict__ mask;
+  const double* __restrict__ reset_noise;
+  double* state;
+  int32_t* years;
+  double* K_env;
+  double* r_env;
+  double* out_obs;
+};
+
+struct RolloutArgs {
+  int64_t n, env_id0, T;
+  uint64_t step0, seed;
+  double r, K, sigma, C, s_reset, K_mean, r_mean, sigma_p, n_actions;
+  int32_t Tmax;
+  uint32_t flags;
+  int32_t discrete;      // fishing-v0: Discrete action space
+  int32_t action_dtype;  // FISHING_POLICY_ACTIONS only
+  double S, msy_q;
+  const double* __restrict__ S_env;
+  const void* __restrict__ actions;
+  const double* __restrict__ noise;
+  int64_t noise_id_div;
+  double* state;
+  int32_t* years;
+  double* K_env;
+  double* r_env;
+  double* __restrict__ out_return;
+  int32_t* __restrict__ out_done_step;
+  double* __restrict__ trace_obs;
+  double* __restrict__ trace_reward;
+  uint8_t* __restrict__ trace_done;
+  double* __restrict__ trace_action;
+};
+
+cudaError_t launch_step(const StepArgs& a, int kind, int act, bool vec, cudaStream_t st);
+cudaError_t launch_reset(const ResetArgs& a, cudaStream_t st);
+cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                              double* out, cudaStream_t st);
+cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r, double K, double C, double sigma,
+                          double z, void* out, cudaStream_t st);
+cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
+cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);
+int64_t reduce_scratch_doubles(int64_t n, int64_t groups);
+cudaError_t launch_reduce(const double* ret, const int32_t* done_step, int64_t n, int64_t groups, double* scratch,
+                          double* out, cudaStream_t st);
+
+}  // namespace fishing

@@ -1,0 +1,398 @@
+// K2: fused T-step rollout.  The state of two environments lives in the registers of one thread for the whole
+// rollout; the policy (constant escapement, MSY, or a caller-supplied action tensor) is applied in-kernel, the
+// Gaussian noise comes from the per-pair Philox stream, and HBM is touched only at entry/exit (plus the optional
+// action tensor / traces).  FP64-pipe bound when no trace is requested.  This is the loop of simulate_mdp
+// (gym_fishing/envs/shared_env.py:29-54) with escapement.predict / msy.predict (models/policies.py:16-31) and
+// BaseFishingEnv.step (envs/base_fishing_env.py:60-81) inlined.
+// K4: fixed-shape reduction of per-env returns to per-group statistics.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "dynamics.cuh"
+#include "kernel_args.cuh"
+#include "philox.cuh"
+
+namespace fishing {
+
+// The two environments a thread owns.  Default layout: adjacent ids (2j, 2j+1) -> 16-byte vector accesses.
+// Sweep layout (noise_id_div = m > 1, env id = replicate*m + level): thread = (replicate pair, level), i.e. ids
+// (2kp*m + j, (2kp+1)*m + j) -> two coalesced 8-byte accesses; both share the level and use the two halves of the
+// replicate pair's noise.
+struct Lanes {
+  int64_t i0, i1;
+  bool vec;
+};
+
+template <typename T2, typename T>
+__device__ __forceinline__ T2 load2(const T* base, const Lanes& L) {
+  if (L.vec) return *reinterpret_cast<const T2*>(base + L.i0);
+  T2 v;
+  v.x = base[L.i0];
+  v.y = base[L.i1];
+  return v;
+}
+template <typename T2, typename T>
+__device__ __forceinline__ T2 load2_stream(const T* base, const Lanes& L) {
+  if (L.vec) return __ldcs(reinterpret_cast<const T2*>(base + L.i0));
+  T2 v;
+  v.x = __ldcs(base + L.i0);
+  v.y = __ldcs(base + L.i1);
+  return v;
+}
+template <typename T2, typename T>
+__device__ __forceinline__ void store2(T* base, const Lanes& L, T a, T b) {
+  if (L.vec) {
+    T2 v;
+    v.x = a;
+    v.y = b;
+    *reinterpret_cast<T2*>(base + L.i0) = v;
+  } else {
+    base[L.i0] = a;
+    base[L.i1] = b;
+  }
+}
+template <typename T2, typename T>
+__device__ __forceinline__ void store2_stream(T* base, const Lanes& L, T a, T b) {
+  if (L.vec) {
+    T2 v;
+    v.x = a;
+    v.y = b;
+    __stcs(reinterpret_cast<T2*>(base + L.i0), v);
+  } else {
+    __stcs(base + L.i0, a);
+    __stcs(base + L.i1, b);
+  }
+}
+
+struct EnvReg {
+  double s, K, r, ret, S, quota_const;
+  int32_t years, done_step;
+  bool frozen;
+};
+
+template <int PM>
+__device__ __forceinline__ double policy_quota_escapement(const RolloutArgs& a, const EnvReg& e, double& action_out) {
+  // escapement.predict, policies.py:27-31, then get_quota of the resulting action (the round trip is not exact)
+  double x = __dadd_rn(e.s, 1.0);
+  if (PM != P_KONE) x = __dmul_rn(x, e.K);
+  const double q = py_max(__dsub_rn(x, e.S), 0.0);
+  if (a.discrete) {
+    const double act = action_discrete<PM>(q, a.n_actions, e.K);
+    action_out = act;
+    const double t = __ddiv_rn(act, a.n_actions);
+    return PM == P_KONE ? t : __dmul_rn(t, e.K);
+  }
+  const double act = action_cts<PM>(q, e.K);
+  action_out = act;
+  return quota_f64<PM>(act, e.K);
+}
+
+template <int PM>
+__device__ __forceinline__ double policy_quota_msy(const RolloutArgs& a, double K, double& action_out) {
+  // msy.predict, policies.py:16-19: action = get_action(msy) every step; constant per environment
+  if (a.discrete) {
+    const double act = action_discrete<PM>(a.msy_q, a.n_actions, K);
+    action_out = act;
+    const double t = __ddiv_rn(act, a.n_actions);
+    return PM == P_KONE ? t : __dmul_rn(t, K);
+  }
+  const double act = action_cts<PM>(a.msy_q, K);
+  action_out = act;
+  return quota_f64<PM>(act, K);
+}
+
+template <int PM>
+__device__ __forceinline__ void load_action_pair(const RolloutArgs& a, const Lanes& L, int64_t t, double K0, double K1,
+                                                 double& q0, double& q1, double& a0, double& a1) {
+  const int64_t off = t * a.n;
+  switch (a.action_dtype) {
+    case FISHING_ACT_F64: {
+      const double2 v = load2_stream<double2>(reinterpret_cast<const double*>(a.actions) + off, L);
+      a0 = v.x; a1 = v.y;
+      q0 = quota_f64<PM>(v.x, K0); q1 = quota_f64<PM>(v.y, K1);
+      break;
+    }
+    case FISHING_ACT_F32: {
+      const float2 v = load2_stream<float2>(reinterpret_cast<const float*>(a.actions) + off, L);
+      a0 = v.x; a1 = v.y;
+      q0 = quota_f32<PM>(v.x, K0); q1 = quota_f32<PM>(v.y, K1);
+      break;
+    }
+    case FISHING_ACT_I32: {
+      const int2 v = load2_stream<int2>(reinterpret_cast<const int32_t*>(a.actions) + off, L);
+      a0 = v.x; a1 = v.y;
+      q0 = quota_int<PM>(v.x, a.n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, K1);
+      break;
+    }
+    default: {
+      const longlong2 v = load2_stream<longlong2>(reinterpret_cast<const long long*>(a.actions) + off, L);
+      a0 = (double)v.x; a1 = (double)v.y;
+      q0 = quota_int<PM>(v.x, a.n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, K1);
+      break;
+    }
+  }
+}
+
+template <int GROWTH, int PM>
+__device__ __forceinline__ void env_advance(const RolloutArgs& a, EnvReg& e, double quota, double z, bool noisy,
+                                            int64_t t, uint64_t gid, double& obs, double& reward, uint8_t& done) {
+  const StepOut o = step_core<GROWTH, PM>(e.s, quota, z, e.r, e.K, a.C, a.sigma, noisy);
+  e.years += 1;
+  done = (e.years > a.Tmax) || o.dead;
+  reward = o.reward;
+  // sequential float64 accumulation, same order as a Python loop; without auto-reset only the first episode counts
+  if ((a.flags & FISHING_AUTO_RESET) || e.done_step < 0) e.ret = __dadd_rn(e.ret, o.reward);
+  e.s = o.s2;
+  obs = o.s2;
+  if (done) {
+    if (e.done_step < 0) e.done_step = (int32_t)t;
+    if (a.flags & FISHING_AUTO_RESET) {
+      e.years = 0;
+      if (PM == P_PERENV) {
+        const Normal2 d = normal_pair(a.seed, gid, a.step0 + (uint64_t)t, FISHING_STREAM_AUTORESET);
+        e.K = v4_param(a.K_mean, a.sigma_p, d.z0);
+        e.r = v4_param(a.r_mean, a.sigma_p, d.z1);
+      }
+      e.s = a.s_reset;
+      obs = a.s_reset;
+    } else if (a.flags & FISHING_FREEZE_DONE) {
+      e.frozen = true;
+    }
+  }
+}
+
+template <int GROWTH, int PM, int POLICY>
+__global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (a.n >> 1)) return;
+  Lanes L;
+  uint64_t noise_pair;
+  const int64_t m = a.noise_id_div;
+  if (m > 1) {
+    const int64_t kp = tid / m, j = tid - kp * m;
+    L.i0 = (2 * kp) * m + j;
+    L.i1 = L.i0 + m;
+    L.vec = false;
+    noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
+  } else {
+    L.i0 = 2 * tid;
+    L.i1 = L.i0 + 1;
+    L.vec = true;
+    noise_pair = ((uint64_t)a.env_id0 >> 1) + (uint64_t)tid;
+  }
+  const uint64_t gid0 = (uint64_t)(a.env_id0 + L.i0), gid1 = (uint64_t)(a.env_id0 + L.i1);
+  const bool ext_noise = a.noise != nullptr;
+  const bool noisy = ext_noise || a.sigma != 0.0;
+  const bool tracing = a.trace_obs || a.trace_reward || a.trace_done || a.trace_action;
+
+  EnvReg e0, e1;
+  {
+    const double2 s = load2<double2>(a.state, L);
+    const int2 y = load2<int2>(a.years, L);
+    e0.s = s.x; e1.s = s.y;
+    e0.years = y.x; e1.years = y.y;
+    if (PM == P_PERENV) {
+      const double2 K = load2<double2>(a.K_env, L), r = load2<double2>(a.r_env, L);
+      e0.K = K.x; e1.K = K.y; e0.r = r.x; e1.r = r.y;
+    } else {
+      e0.K = e1.K = a.K;
+      e0.r = e1.r = a.r;
+    }
+    e0.S = e1.S = a.S;
+    if (POLICY == FISHING_POLICY_ESCAPEMENT && a.S_env) {
+      const double2 S = load2<double2>(a.S_env, L);
+      e0.S = S.x; e1.S = S.y;
+    }
+    e0.ret = e1.ret = 0.0;
+    e0.done_step = e1.done_step = -1;
+    e0.frozen = e1.frozen = false;
+    e0.quota_const = e1.quota_const = 0.0;
+  }
+  double act0 = 0.0, act1 = 0.0;
+  if (POLICY == FISHING_POLICY_MSY && PM != P_PERENV) {
+    e0.quota_const = policy_quota_msy<PM>(a, e0.K, act0);
+    e1.quota_const = e0.quota_const;
+    act1 = act0;
+  }
+
+  for (int64_t t = 0; t < a.T; ++t) {
+    if (e0.frozen && e1.frozen && !tracing) break;
+    double z0 = 0.0, z1 = 0.0;
+    if (ext_noise) {
+      const double2 z = load2_stream<double2>(a.noise + t * a.n, L);
+      z0 = z.x; z1 = z.y;
+    } else if (noisy) {
+      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      z0 = d.z0; z1 = d.z1;
+    }
+    double q0, q1;
+    if (POLICY == FISHING_POLICY_ACTIONS) {
+      load_action_pair<PM>(a, L, t, e0.K, e1.K, q0, q1, act0, act1);
+    } else if (POLICY == FISHING_POLICY_ESCAPEMENT) {
+      q0 = policy_quota_escapement<PM>(a, e0, act0);
+      q1 = policy_quota_escapement<PM>(a, e1, act1);
+    } else {
+      if (PM == P_PERENV) {  // per-env K changes at auto-reset: recompute
+        q0 = policy_quota_msy<PM>(a, e0.K, act0);
+        q1 = policy_quota_msy<PM>(a, e1.K, act1);
+      } else {
+        q0 = e0.quota_const;
+        q1 = e1.quota_const;
+      }
+    }
+    double o0 = e0.s, o1 = e1.s, r0 = 0.0, r1 = 0.0;
+    uint8_t d0 = 1, d1 = 1;
+    if (!e0.frozen) env_advance<GROWTH, PM>(a, e0, q0, z0, noisy, t, gid0, o0, r0, d0);
+    if (!e1.frozen) env_advance<GROWTH, PM>(a, e1, q1, z1, noisy, t, gid1, o1, r1, d1);
+    if (tracing) {
+      const int64_t off = t * a.n;
+      if (a.trace_obs) store2_stream<double2>(a.trace_obs + off, L, o0, o1);
+      if (a.trace_reward) store2_stream<double2>(a.trace_reward + off, L, r0, r1);
+      if (a.trace_done) store2_stream<uchar2>(a.trace_done + off, L, d0, d1);
+      if (a.trace_action) store2_stream<double2>(a.trace_action + off, L, act0, act1);
+    }
+  }
+
+  store2<double2>(a.state, L, e0.s, e1.s);
+  store2<int2>(a.years, L, e0.years, e1.years);
+  if (PM == P_PERENV) {
+    store2<double2>(a.K_env, L, e0.K, e1.K);
+    store2<double2>(a.r_env, L, e0.r, e1.r);
+  }
+  if (a.out_return) store2<double2>(a.out_return, L, e0.ret, e1.ret);
+  if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
+}
+
+template <int GROWTH, int PM>
+static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream_t st) {
+  const int64_t threads = a.n >> 1;
+  const int block = 128;
+  const int64_t grid = (threads + block - 1) / block;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  switch (policy) {
+    case FISHING_POLICY_ACTIONS: rollout_kernel<GROWTH, PM, FISHING_POLICY_ACTIONS><<<(int)grid, block, 0, st>>>(a); break;
+    case FISHING_POLICY_ESCAPEMENT: rollout_kernel<GROWTH, PM, FISHING_POLICY_ESCAPEMENT><<<(int)grid, block, 0, st>>>(a); break;
+    default: rollout_kernel<GROWTH, PM, FISHING_POLICY_MSY><<<(int)grid, block, 0, st>>>(a); break;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st) {
+  if (kind == FISHING_V4) return launch_rollout_p<LOGISTIC, P_PERENV>(a, policy, st);
+  const bool kone = a.K == 1.0;
+  if (kind == FISHING_V2)
+    return kone ? launch_rollout_p<TIPPING, P_KONE>(a, policy, st) : launch_rollout_p<TIPPING, P_UNIFORM>(a, policy, st);
+  return kone ? launch_rollout_p<LOGISTIC, P_KONE>(a, policy, st) : launch_rollout_p<LOGISTIC, P_UNIFORM>(a, policy, st);
+}
+
+// ------------------------------------------------------------------------------------------------ K4: statistics
+// View ret[n] as a matrix [rows = n / groups, groups].  Pass 1: each thread owns one column of a 64-row chunk and adds
+// the rows in order -> partial[chunk][group][3].  Pass 2: pairwise (binary-tree) combination of the chunk partials in
+// a fixed order.  No atomics, so the result depends only on (n, groups), never on the grid or on timing; contiguous
+// power-of-two shards of the row range are subtrees of the same tree (multi-GPU results combine exactly).
+constexpr int REDUCE_ROWS = 64;
+
+__global__ void __launch_bounds__(256) reduce_pass1(const double* __restrict__ ret, const int32_t* __restrict__ done_step,
+                                                     int64_t rows, int64_t groups, double* __restrict__ partial) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t chunk = blockIdx.y;
+  if (g >= groups) return;
+  const int64_t r0 = chunk * REDUCE_ROWS;
+  const int64_t r1 = (r0 + REDUCE_ROWS < rows) ? r0 + REDUCE_ROWS : rows;
+  double s = 0.0, s2 = 0.0, nd = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const double v = ret[r * groups + g];
+    s = __dadd_rn(s, v);
+    s2 = __dadd_rn(s2, __dmul_rn(v, v));
+    if (done_step && done_step[r * groups + g] >= 0) nd += 1.0;
+  }
+  double* p = partial + (chunk * groups + g) * 3;
+  p[0] = s;
+  p[1] = s2;
+  p[2] = nd;
+}
+
+__global__ void __launch_bounds__(256) reduce_pass2(double* __restrict__ partial, int64_t chunks, int64_t groups,
+                                                     double* __restrict__ out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  // adjacent pairing (2c, 2c+1) -> c, level by level, in place: p[c] is consumed at iteration c/2 <= c before it is
+  // overwritten.  An odd leftover is carried up unchanged (x + nothing), so aligned power-of-two sub-ranges are
+  // exact subtrees.
+  while (chunks > 1) {
+    const int64_t next = (chunks + 1) >> 1;
+    for (int64_t c = 0; c < next; ++c) {
+      double* d = partial + (c * groups + g) * 3;
+      const double* p = partial + ((2 * c) * groups + g) * 3;
+      if (2 * c + 1 < chunks) {
+        const double* q = partial + ((2 * c + 1) * groups + g) * 3;
+        const double v0 = __dadd_rn(p[0], q[0]), v1 = __dadd_rn(p[1], q[1]), v2 = __dadd_rn(p[2], q[2]);
+        d[0] = v0; d[1] = v1; d[2] = v2;
+      } else {
+        const double v0 = p[0], v1 = p[1], v2 = p[2];
+        d[0] = v0; d[1] = v1; d[2] = v2;
+      }
+    }
+    chunks = next;
+  }
+  out[g * 3 + 0] = partial[g * 3 + 0];
+  out[g * 3 + 1] = partial[g * 3 + 1];
+  out[g * 3 + 2] = partial[g * 3 + 2];
+}
+
+// groups == 1 convenience: the columns of the internal 256-wide view are folded by one block with the same adjacent
+// pairwise tree.
+__global__ void __launch_bounds__(256) reduce_fold_columns(const double* __restrict__ cols, int ncols, double* __restrict__ out) {
+  __shared__ double sh[256 * 3];
+  const int t = threadIdx.x;
+  for (int k = 0; k < 3; ++k) sh[t * 3 + k] = t < ncols ? cols[t * 3 + k] : 0.0;
+  __syncthreads();
+  for (int width = 256; width > 1; width >>= 1) {
+    double v[3];
+    const bool act = t < width / 2;
+    if (act)
+      for (int k = 0; k < 3; ++k) v[k] = __dadd_rn(sh[(2 * t) * 3 + k], sh[(2 * t + 1) * 3 + k]);
+    __syncthreads();
+    if (act)
+      for (int k = 0; k < 3; ++k) sh[t * 3 + k] = v[k];
+    __syncthreads();
+  }
+  if (t < 3) out[t] = sh[t];
+}
+
+constexpr int VIRTUAL_GROUPS = 256;
+static int64_t virtual_groups(int64_t n, int64_t groups) {
+  return (groups == 1 && n % VIRTUAL_GROUPS == 0 && n >= VIRTUAL_GROUPS) ? VIRTUAL_GROUPS : groups;
+}
+
+int64_t reduce_chunks(int64_t n, int64_t groups) {
+  const int64_t rows = n / virtual_groups(n, groups);
+  return (rows + REDUCE_ROWS - 1) / REDUCE_ROWS;
+}
+
+int64_t reduce_scratch_doubles(int64_t n, int64_t groups) {
+  const int64_t vg = virtual_groups(n, groups);
+  return (reduce_chunks(n, groups) + 1) * vg * 3;
+}
+
+cudaError_t launch_reduce(const double* ret, const int32_t* done_step, int64_t n, int64_t groups, double* scratch,
+                          double* out, cudaStream_t st) {
+  const int64_t vg = virtual_groups(n, groups);
+  const int64_t rows = n / vg;
+  const int64_t chunks = reduce_chunks(n, groups);
+  if (chunks > 65535) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)((vg + 255) / 256), (unsigned)chunks);
+  reduce_pass1<<<grid, 256, 0, st>>>(ret, done_step, rows, vg, scratch);
+  count_launch();
+  double* cols = vg == groups ? out : scratch + chunks * vg * 3;
+  reduce_pass2<<<(unsigned)((vg + 255) / 256), 256, 0, st>>>(scratch, chunks, vg, cols);
+  count_launch();
+  if (vg != groups) {
+    reduce_fold_columns<<<1, 256, 0, st>>>(cols, (int)vg, out);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fishing

@@ -1,0 +1,384 @@
+// K1: the lock-step single-step kernel, K3: reset / fishing-v4 parameter draws, plus the noise exporter and BMSY.
+// HBM-bound structure-of-arrays float64 streaming: per env-step the kernel reads state(8) + action(8|4) +
+// years(4) and writes obs(8) + reward(8) + done(1) + years(4); see DESIGN.md for the byte accounting.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "dynamics.cuh"
+#include "kernel_args.cuh"
+#include "philox.cuh"
+
+namespace fishing {
+
+// One environment: everything after the loads.  Returns the values to store.
+struct EnvResult {
+  double obs, reward, K, r;
+  int32_t years;
+  uint8_t done;
+  bool reset_fired;
+  double terminal, stock, harvest;
+};
+
+template <int GROWTH, int PM, int ACT>
+__device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, double s, typename ActT<ACT>::type act,
+                                             double z, bool noisy, int32_t years, double K, double r) {
+  const double quota = quota_of<PM, ACT>(act, a.n_actions, K);
+  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy);
+  EnvResult e;
+  e.years = years + 1;                                   // base_fishing_env.py:75
+  e.done = (e.years > a.Tmax) || o.dead;                 // :76-79
+  e.obs = o.s2;
+  e.reward = o.reward;
+  e.K = K;
+  e.r = r;
+  e.reset_fired = false;
+  e.terminal = o.s2;
+  e.stock = o.stock;
+  e.harvest = o.harvest;
+  if ((a.flags & FISHING_AUTO_RESET) && e.done) {        // SB3 VecEnv: reset inside the step that ended the episode
+    e.reset_fired = true;
+    e.years = 0;
+    if (PM == P_PERENV) {                                // FishingModelError.reset, fishing_model_error.py:41-48
+      double zK, zr;
+      if (a.reset_noise) {
+        zK = a.reset_noise[i];
+        zr = a.reset_noise[a.n + i];
+      } else {
+        const Normal2 d = normal_pair(a.seed, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET);
+        zK = d.z0;
+        zr = d.z1;
+      }
+      e.K = v4_param(a.K_mean, a.sigma_p, zK);
+      e.r = v4_param(a.r_mean, a.sigma_p, zr);
+    }
+    e.obs = a.s_reset;
+  }
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------ K1, vector path
+// Each thread owns PAIRS of adjacent environments (2j, 2j+1): 16-byte loads/stores for the float64 arrays, one
+// Philox block + one Box-Muller per pair.  UNROLL independent pairs per thread keep several loads in flight.
+template <int GROWTH, int PM, int ACT, int UNROLL>
+__global__ void __launch_bounds__(256) step_kernel_vec2(const StepArgs a) {
+  using AT2 = typename ActT<ACT>::vec2;
+  const int64_t npairs = a.n >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool ext_noise = a.noise != nullptr;
+  const bool noisy = ext_noise || a.sigma != 0.0;
+  const uint64_t pair0 = (uint64_t)a.env_id0 >> 1;
+
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < npairs; base += stride * UNROLL) {
+    double2 s[UNROLL], z[UNROLL], Kv[UNROLL], rv[UNROLL];
+    AT2 act[UNROLL];
+    int2 yr[UNROLL];
+    bool live[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t j = base + u * stride;
+      live[u] = j < npairs;
+      if (live[u]) {
+        act[u] = ld_stream(reinterpret_cast<const AT2*>(a.action) + j);
+        if (ext_noise) z[u] = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
+        s[u] = reinterpret_cast<const double2*>(a.state_in)[j];
+        yr[u] = reinterpret_cast<const int2*>(a.years)[j];
+        if (PM == P_PERENV) {
+          Kv[u] = reinterpret_cast<const double2*>(a.K_env)[j];
+          rv[u] = reinterpret_cast<const double2*>(a.r_env)[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (!live[u]) continue;
+      const int64_t j = base + u * stride;
+      if (PM != P_PERENV) {
+        Kv[u] = make_double2(a.K, a.K);
+        rv[u] = make_double2(a.r, a.r);
+      }
+      if (!ext_noise) {
+        if (noisy) {
+          const Normal2 d = normal_pair(a.seed, pair0 + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
+          z[u] = make_double2(d.z0, d.z1);
+        } else {
+          z[u] = make_double2(0.0, 0.0);
+        }
+      }
+      const EnvResult e0 = advance<GROWTH, PM, ACT>(a, 2 * j, s[u].x, act[u].x, z[u].x, noisy, yr[u].x, Kv[u].x, rv[u].x);
+      const EnvResult e1 = advance<GROWTH, PM, ACT>(a, 2 * j + 1, s[u].y, act[u].y, z[u].y, noisy, yr[u].y, Kv[u].y, rv[u].y);
+      reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
+      st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
+      st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
+      reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
+      if (a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
+      if (a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
+      if (e0.reset_fired | e1.reset_fired) {
+        if (a.out_terminal) {
+          if (e0.reset_fired) a.out_terminal[2 * j] = e0.terminal;
+          if (e1.reset_fired) a.out_terminal[2 * j + 1] = e1.terminal;
+        }
+        if (PM == P_PERENV) {
+          reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
+          reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1, scalar path
+// Same results for odd n / odd env_id0 / unaligned slices: one environment per thread, which recomputes its pair's
+// Philox block and picks its half.
+template <int GROWTH, int PM, int ACT>
+__global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
+  using AT = typename ActT<ACT>::type;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool ext_noise = a.noise != nullptr;
+  const bool noisy = ext_noise || a.sigma != 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const uint64_t gid = (uint64_t)(a.env_id0 + i);
+    double z = 0.0;
+    if (ext_noise) {
+      z = a.noise[i];
+    } else if (noisy) {
+      const Normal2 d = normal_pair(a.seed, gid >> 1, a.step_idx, FISHING_STREAM_STEP);
+      z = (gid & 1) ? d.z1 : d.z0;
+    }
+    const double K = PM == P_PERENV ? a.K_env[i] : a.K;
+    const double r = PM == P_PERENV ? a.r_env[i] : a.r;
+    const EnvResult e = advance<GROWTH, PM, ACT>(a, i, a.state_in[i], reinterpret_cast<const AT*>(a.action)[i], z, noisy,
+                                                 a.years[i], K, r);
+    a.out_obs[i] = e.obs;
+    a.out_reward[i] = e.reward;
+    a.out_done[i] = e.done;
+    a.years[i] = e.years;
+    if (a.out_stock) a.out_stock[i] = e.stock;
+    if (a.out_harvest) a.out_harvest[i] = e.harvest;
+    if (e.reset_fired) {
+      if (a.out_terminal) a.out_terminal[i] = e.terminal;
+      if (PM == P_PERENV) {
+        a.K_env[i] = e.K;
+        a.r_env[i] = e.r;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3: reset
+__global__ void __launch_bounds__(256) reset_kernel(const ResetArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    if (a.mask && !a.mask[i]) {
+      if (a.out_obs && a.out_obs != a.state) a.out_obs[i] = a.state[i];
+      continue;
+    }
+    if (a.per_env) {
+      double zK, zr;
+      if (a.reset_noise) {
+        zK = a.reset_noise[i];
+        zr = a.reset_noise[a.n + i];
+      } else {
+        const Normal2 d = normal_pair(a.seed, (uint64_t)(a.env_id0 + i), a.epoch, FISHING_STREAM_RESET);
+        zK = d.z0;
+        zr = d.z1;
+      }
+      a.K_env[i] = v4_param(a.K_mean, a.sigma_p, zK);
+      a.r_env[i] = v4_param(a.r_mean, a.sigma_p, zr);
+    }
+    a.state[i] = a.s_reset;
+    a.years[i] = 0;
+    if (a.out_obs) a.out_obs[i] = a.s_reset;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ noise exporter
+__global__ void __launch_bounds__(256) noise_fill_kernel(uint64_t seed, int32_t stream_id, int64_t n, int64_t env_id0,
+                                                          uint64_t step0, int64_t T, double* __restrict__ out) {
+  const int64_t total = n * T;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    const int64_t t = k / n, i = k - t * n;
+    const uint64_t gid = (uint64_t)(env_id0 + i);
+    if (stream_id == FISHING_STREAM_STEP) {
+      const Normal2 d = normal_pair(seed, gid >> 1, step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      out[k] = (gid & 1) ? d.z1 : d.z0;
+    } else {
+      const Normal2 d = normal_pair(seed, gid, step0 + (uint64_t)t, (uint32_t)stream_id);
+      out[(t * 2 + 0) * n + i] = d.z0;
+      out[(t * 2 + 1) * n + i] = d.z1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BMSY
+// policies.py:51-67.  The reference evaluates population_draw ONCE on the whole float32 grid, so for v0/v1/v2 every
+// operation is a float32 operation (K, r, C are Python numbers and take the array's dtype); for v4 K and r are
+// np.float64 scalars and the grid is promoted to float64.  One block; argmax keeps the FIRST maximum like np.argmax.
+template <typename F>
+__device__ __forceinline__ F f_exp(F v);
+template <>
+__device__ __forceinline__ float f_exp<float>(float v) { return (float)exp((double)v); }
+template <>
+__device__ __forceinline__ double f_exp<double>(double v) { return exp(v); }
+
+// population_draw on a value of dtype F (float32 when the reference's array is float32 and r, K, C, sigma, z are
+// Python numbers, which then take the array's dtype under numpy's promotion rules).
+template <typename F>
+__device__ __forceinline__ F growth_f(int kind, F x0, F r, F K, F C, F sigma, F z) {
+  // float and double arithmetic below is written with the non-contracting intrinsics of the matching width
+  auto mul = [](F p, F q) -> F { if constexpr (sizeof(F) == 4) return __fmul_rn(p, q); else return __dmul_rn(p, q); };
+  auto add = [](F p, F q) -> F { if constexpr (sizeof(F) == 4) return __fadd_rn(p, q); else return __dadd_rn(p, q); };
+  auto sub = [](F p, F q) -> F { if constexpr (sizeof(F) == 4) return __fsub_rn(p, q); else return __dsub_rn(p, q); };
+  auto div = [](F p, F q) -> F { if constexpr (sizeof(F) == 4) return __fdiv_rn(p, q); else return __ddiv_rn(p, q); };
+  const F room = sub((F)1, div(x0, K));
+  const F noise = mul(mul(x0, sigma), z);
+  F g;
+  if (kind == FISHING_V2) {
+    const F e = add(mul(mul(r, room), sub(x0, C)), noise);
+    g = mul(x0, f_exp<F>(e));
+  } else {
+    g = add(add(x0, mul(mul(r, x0), room)), noise);
+  }
+  return (g > (F)0 || g != g) ? g : (F)0;
+}
+
+template <typename F>
+__device__ __forceinline__ F growth_minus_x(int kind, F x0, F r, F K, F C) {
+  const F g = growth_f<F>(kind, x0, r, K, C, (F)0, (F)0);  // sigma forced to 0, policies.py:61-63
+  if constexpr (sizeof(F) == 4) return __fsub_rn(g, x0);
+  else return __dsub_rn(g, x0);
+}
+
+// Stand-alone BaseFishingEnv.population_draw on an array (one scalar z for the whole array, as the reference draws it).
+template <typename F>
+__global__ void __launch_bounds__(256) growth_kernel(int kind, int64_t n, const F* __restrict__ x, double r, double K,
+                                                      double C, double sigma, double z, F* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = growth_f<F>(kind, x[i], (F)r, (F)K, (F)C, (F)sigma, (F)z);
+}
+
+// np.linspace(float32(-1), float32(1), num, dtype=float32) evaluates arange(num, dtype=f32) * (f32(2) / (num-1)) +
+// f32(-1) entirely in float32 and then overwrites the last point with the stop value (numpy/_core/function_base.py).
+__device__ __forceinline__ float linspace_f32(int i, int num) {
+  if (i == num - 1) return 1.0f;
+  return __fadd_rn(__fmul_rn((float)i, __fdiv_rn(2.0f, (float)(num - 1))), -1.0f);
+}
+
+template <typename F>
+__global__ void __launch_bounds__(1024) bmsy_kernel(int kind, double r_, double K_, double C_, double* out) {
+  constexpr int NGRID = 10001;
+  __shared__ double best_v[1024];
+  __shared__ int best_i[1024];
+  const F r = (F)r_, K = (F)K_, C = (F)C_;
+  double bv = -INFINITY;
+  int bi = NGRID;
+  bool nan_seen = false;
+  for (int i = threadIdx.x; i < NGRID; i += blockDim.x) {
+    const float g32 = linspace_f32(i, NGRID);
+    F x0;
+    if constexpr (sizeof(F) == 4) x0 = __fmul_rn(__fadd_rn(g32, 1.0f), K);        // (np.float32 + 1) * K, float32
+    else x0 = __dmul_rn((double)__fadd_rn(g32, 1.0f), K);                         // float32 sum, float64 product
+    const double v = (double)growth_minus_x<F>(kind, x0, r, K, C);
+    if (v != v) {  // np.argmax returns the first NaN
+      if (!nan_seen || i < bi) { bi = nan_seen ? min(bi, i) : i; nan_seen = true; bv = INFINITY; }
+    } else if (!nan_seen && (v > bv || (v == bv && i < bi))) {
+      bv = v;
+      bi = i;
+    }
+  }
+  best_v[threadIdx.x] = bv;
+  best_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      const double ov = best_v[threadIdx.x + w];
+      const int oi = best_i[threadIdx.x + w];
+      if (ov > best_v[threadIdx.x] || (ov == best_v[threadIdx.x] && oi < best_i[threadIdx.x])) {
+        best_v[threadIdx.x] = ov;
+        best_i[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int i = best_i[0];
+    const float g32 = linspace_f32(i, NGRID);
+    F S;
+    if constexpr (sizeof(F) == 4) S = __fmul_rn(__fadd_rn(g32, 1.0f), K);
+    else S = __dmul_rn((double)__fadd_rn(g32, 1.0f), K);
+    out[0] = (double)S;
+    out[1] = (double)growth_minus_x<F>(kind, S, r, K, C);  // msy.__init__, policies.py:9-12
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
+  const int64_t need = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * max_blocks_per_sm;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+template <int GROWTH, int PM, int ACT>
+static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
+  constexpr int UNROLL = 2;
+  if (vec) {
+    const int64_t npairs = a.n >> 1;
+    const int grid = grid_for((npairs + UNROLL - 1) / UNROLL, 256, 8);
+    step_kernel_vec2<GROWTH, PM, ACT, UNROLL><<<grid, 256, 0, st>>>(a);
+  } else {
+    const int grid = grid_for(a.n, 256, 8);
+    step_kernel_scalar<GROWTH, PM, ACT><<<grid, 256, 0, st>>>(a);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int GROWTH, int PM>
+static cudaError_t launch_step_a(const StepArgs& a, int act, bool vec, cudaStream_t st) {
+  switch (act) {
+    case FISHING_ACT_F64: return launch_step_t<GROWTH, PM, FISHING_ACT_F64>(a, vec, st);
+    case FISHING_ACT_F32: return launch_step_t<GROWTH, PM, FISHING_ACT_F32>(a, vec, st);
+    case FISHING_ACT_I32: return launch_step_t<GROWTH, PM, FISHING_ACT_I32>(a, vec, st);
+    default: return launch_step_t<GROWTH, PM, FISHING_ACT_I64>(a, vec, st);
+  }
+}
+
+cudaError_t launch_step(const StepArgs& a, int kind, int act, bool vec, cudaStream_t st) {
+  if (kind == FISHING_V4) return launch_step_a<LOGISTIC, P_PERENV>(a, act, vec, st);
+  const bool kone = a.K == 1.0;
+  if (kind == FISHING_V2)
+    return kone ? launch_step_a<TIPPING, P_KONE>(a, act, vec, st) : launch_step_a<TIPPING, P_UNIFORM>(a, act, vec, st);
+  return kone ? launch_step_a<LOGISTIC, P_KONE>(a, act, vec, st) : launch_step_a<LOGISTIC, P_UNIFORM>(a, act, vec, st);
+}
+
+cudaError_t launch_reset(const ResetArgs& a, cudaStream_t st) {
+  reset_kernel<<<grid_for(a.n, 256, 8), 256, 0, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                              double* out, cudaStream_t st) {
+  noise_fill_kernel<<<grid_for(n * T, 256, 8), 256, 0, st>>>(seed, stream_id, n, env_id0, step0, T, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r, double K, double C, double sigma,
+                          double z, void* out, cudaStream_t st) {
+  const int grid = grid_for(n, 256, 8);
+  if (f32) growth_kernel<float><<<grid, 256, 0, st>>>(kind, n, (const float*)x, r, K, C, sigma, z, (float*)out);
+  else growth_kernel<double><<<grid, 256, 0, st>>>(kind, n, (const double*)x, r, K, C, sigma, z, (double*)out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st) {
+  if (f64) bmsy_kernel<double><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);
+  else bmsy_kernel<float><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace fishing

@@ -1,0 +1,56 @@
+"""Classical fisheries policies with the reference's protocol `model.predict(obs, **kw) -> (action, state)`
+(gym_fishing/models/policies.py:4-31,51-67).  The interactive `user_action` policy is out of scope.
+
+BMSY runs on the device (fishing_bmsy: the 10001-point float32 grid, deterministic growth and first-argmax in one
+kernel).  To keep numpy's global random stream in step with the reference when the env draws its noise there, BMSY
+consumes the one normal draw the reference's vectorised population_draw() would have consumed (policies.py:63) and
+resets the env (policies.py:66)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _native as nat
+from ..engine import bmsy as _bmsy_kernel
+
+
+def BMSY(env):
+    """Stock size with maximum deterministic surplus production.  np.float32 for v0/v1/v2, np.float64 for v4,
+    exactly as the reference returns it.  Resets the environment."""
+    kind = env._kind
+    K_f64 = kind == nat.V4 or isinstance(env.K, np.floating) or isinstance(env.r, np.floating)
+    if getattr(env, "_noise_mode", "philox") == "numpy":
+        env._draw()
+    S, _ = _bmsy_kernel(kind, r=env.r, K=env.K, C=getattr(env, "C", 0.5), K_is_f64=K_f64)
+    env.reset()
+    return np.float64(S) if K_f64 else np.float32(S)
+
+
+class msy:
+    """Constant quota equal to the surplus production at BMSY."""
+
+    def __init__(self, env, **kwargs):
+        self.env = env
+        self.S = BMSY(env)
+        keep = env.sigma
+        env.fish_population = self.S
+        env.sigma = 0
+        try:
+            self.msy = env.population_draw() - self.S
+        finally:
+            env.sigma = keep
+        env.reset()
+
+    def predict(self, obs, **kwargs):
+        return self.env.get_action(self.msy), obs
+
+
+class escapement:
+    """Constant escapement: harvest everything above S = BMSY."""
+
+    def __init__(self, env, **kwargs):
+        self.env = env
+        self.S = BMSY(env)
+
+    def predict(self, obs, **kwargs):
+        x = self.env.get_fish_population(obs)
+        return self.env.get_action(max(x - self.S, 0.0)), obs

@@ -1,0 +1,108 @@
+"""Rollout recording and reporting helpers with the reference's outputs (gym_fishing/envs/shared_env.py:8-127):
+simulate_mdp / simulate_mdp_vec tables with columns [time, state, action, reward, rep], estimate_policyfn, and the
+matplotlib plots (only if matplotlib is installed)."""
+from __future__ import annotations
+
+import numpy as np
+from pandas import DataFrame
+
+COLUMNS = ["time", "state", "action", "reward", "rep"]
+
+
+def simulate_mdp(env, model, reps=1):
+    """Policy/env loop of at most env.Tmax steps per repetition.  Row t holds the stock BEFORE step t together with
+    the quota and reward of step t-1 (one-step lag, shared_env.py:37-38,49), and the loop stops after a done step."""
+    rows = []
+    for rep in range(int(reps)):
+        obs = env.reset()
+        last_quota, last_reward = 0.0, 0.0
+        t = 0
+        while t < env.Tmax:
+            rows.append([t, env.get_fish_population(obs), last_quota, last_reward, rep])
+            action, _ = model.predict(obs)
+            obs, last_reward, done, _ = env.step(action)
+            if isinstance(action, np.ndarray):
+                action = action[0]
+            if isinstance(last_reward, np.ndarray):
+                last_reward = last_reward[0]
+            last_quota = env.get_quota(action)
+            t += 1
+            if done:
+                break
+    return DataFrame(rows, columns=COLUMNS)
+
+
+def simulate_mdp_vec(env, model, n_eval_episodes):
+    """The reference's VecEnv consumer (shared_env.py:57-79) rebuilt on whole-batch arrays: one row per (t, env) for
+    t = 0..Tmax, `rep` numbering episodes across repetitions.  Works with FishingVecEnv in either io mode and with
+    any object following the SB3 VecEnv protocol."""
+    if n_eval_episodes % env.num_envs != 0:
+        raise AssertionError("number of evaluations needs to be divisible by the number of parallel environments")
+    n = env.num_envs
+    reps = n_eval_episodes // n
+    Tmax = env.get_attr("Tmax")[0]
+    K = np.asarray(env.get_attr("K"), dtype=np.float64)
+    chunks = []
+
+    def to_np(a):
+        return a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+
+    for rep in range(reps):
+        obs = env.reset()
+        state = None
+        done = np.zeros(n, dtype=bool)
+        action = np.full((n, 1), env.action_space.low[0] if hasattr(env.action_space, "low") else 0)
+        reward = np.zeros(n)
+        for t in range(Tmax + 1):
+            x = (to_np(obs).reshape(n) + 1) * K
+            chunks.append(np.column_stack([np.full(n, t), x, to_np(action).reshape(n), to_np(reward).reshape(n),
+                                           rep * n + np.arange(n)]))
+            if t == Tmax:
+                break
+            action, state = model.predict(obs, state=state, mask=done)
+            obs, reward, done, _ = env.step(action)
+    df = DataFrame(np.concatenate(chunks), columns=COLUMNS)
+    return df.astype({"time": int, "rep": int})
+
+
+def estimate_policyfn(env, model, reps=1, n=50):
+    """Policy as a function of the stock over n observation points (shared_env.py:82-102)."""
+    grid = np.linspace(env.observation_space.low, env.observation_space.high, num=n, dtype=env.observation_space.dtype)
+    rows = []
+    for rep in range(int(reps)):
+        for obs in grid:
+            action, _ = model.predict(obs)
+            if isinstance(action, np.ndarray):
+                action = action[0]
+            rows.append([env.get_fish_population(obs), env.get_quota(action), rep])
+    return DataFrame(rows, columns=["state", "action", "rep"])
+
+
+def _plt():
+    try:
+        import matplotlib.pyplot as plt  # noqa: WPS433
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError("plotting needs matplotlib, which is not installed") from e
+    return plt
+
+
+def plot_mdp(self, df, output="results.png"):
+    plt = _plt()
+    fig, axs = plt.subplots(3, 1)
+    for rep, g in df.groupby("rep"):
+        axs[0].plot(g.time, g.state, color="blue", alpha=0.3)
+        axs[1].plot(g.time, g.action, color="blue", alpha=0.3)
+        axs[2].plot(g.time, np.cumsum(g.reward), color="blue", alpha=0.3)
+    for ax, lab in zip(axs, ("state", "action", "reward")):
+        ax.set_ylabel(lab)
+    fig.tight_layout()
+    plt.savefig(output)
+    plt.close("all")
+
+
+def plot_policyfn(self, df, output="policy.png"):
+    plt = _plt()
+    for rep, g in df.groupby("rep"):
+        plt.plot(g.state, g.state - g.action, color="blue")
+    plt.savefig(output)
+    plt.close("all")

@@ -1,0 +1,340 @@
+"""FishingVecEnv -- the batched, lock-step environment class (new; the reference has none, it only *consumes* a
+stable-baselines3 VecEnv in simulate_mdp_vec, gym_fishing/envs/shared_env.py:15-26,57-79).
+
+It satisfies that consumer and the SB3 VecEnv duck type: num_envs, observation_space, action_space, reset(),
+step(actions) / step_async + step_wait, get_attr, set_attr, env_method, seed, close, auto-reset on done with
+infos[i]["terminal_observation"].  Two I/O modes:
+
+  * io="torch" (default): actions / observations / rewards / dones are CUDA tensors; zero copies, the kernels run on
+    the current torch stream.  `step_into(...)` writes straight into slices of a caller-owned rollout buffer.
+  * io="numpy": host arrays in and out through the library's pinned, chunk-pipelined host front end
+    (fishing_vec_* in include/fishing_b200.h) -- what a stable-baselines3 loop or the reference's own
+    simulate_mdp_vec sees.
+
+All dynamics run in the sm_100a kernels of libfishing_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+
+from . import _native as nat
+from .engine import EnvBatch
+from .spaces import Discrete, unit_box
+
+_CTOR_KEYS = {
+    nat.V0: ("r", "K", "sigma", "n_actions", "init_state", "Tmax"),
+    nat.V1: ("r", "K", "sigma", "init_state", "Tmax"),
+    nat.V2: ("r", "K", "C", "sigma", "init_state", "Tmax"),
+    nat.V4: ("K_mean", "r_mean", "price", "sigma", "sigma_p", "init_state", "Tmax"),
+}
+
+
+def normalise_kwargs(kind, kw):
+    """Map the reference's constructor keywords (fishing_env.py:7-16, fishing_cts_env.py:5-7,
+    fishing_tipping_env.py:7-16, fishing_model_error.py:9-19) to engine parameters."""
+    kw = dict(kw)
+    kw.pop("file", None)
+    bad = set(kw) - set(_CTOR_KEYS[kind])
+    if bad:
+        raise TypeError(f"unexpected keyword argument(s) {sorted(bad)} for this environment id")
+    out = dict(r=0.3, K=1.0, sigma=0.0, C=0.5, x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1)
+    if kind == nat.V4:
+        out["r"] = kw.get("r_mean", 0.3)
+        out["K"] = kw.get("K_mean", 1.0)
+    else:
+        out["r"] = kw.get("r", 0.3)
+        out["K"] = kw.get("K", 1)
+    for k in ("sigma", "C", "Tmax", "n_actions", "sigma_p"):
+        if k in kw:
+            out[k] = kw[k]
+    out["x0"] = kw.get("init_state", 0.75)
+    return out
+
+
+class LazyInfos:
+    """Sequence of per-env info dicts materialised on access (a list of 2^20 dicts per step would dominate the run
+    time).  infos[i] == {"terminal_observation": array([s])} if env i finished in this step, else {}."""
+
+    def __init__(self, done, terminal):
+        self._done, self._terminal = done, terminal
+
+    def __len__(self):
+        return len(self._done)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if bool(self._done[i]) and self._terminal is not None:
+            t = self._terminal[i]
+            t = t.reshape(1) if hasattr(t, "reshape") else np.array([t])
+            return {"terminal_observation": t}
+        return {}
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _PinnedArray:
+    """numpy view over page-locked host memory from fishing_host_alloc (freed with the owner)."""
+
+    def __init__(self, n, dtype):
+        dtype = np.dtype(dtype)
+        self.nbytes = max(1, n * dtype.itemsize)
+        p = ct.c_void_p()
+        nat.check(nat.lib().fishing_host_alloc(ct.byref(p), self.nbytes), "fishing_host_alloc")
+        self.ptr = p
+        buf = (ct.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n)
+
+    def free(self):
+        if self.ptr is not None:
+            nat.lib().fishing_host_free(self.ptr)
+            self.ptr = None
+
+
+class FishingVecEnv:
+    def __init__(self, env_id="fishing-v1", num_envs=1, *, device="cuda", io="torch", seed=0, auto_reset=True,
+                 env_id_offset=0, **env_kwargs):
+        if env_id not in nat.KIND_OF_ID:
+            raise KeyError(f"unknown environment id {env_id!r}")
+        if io not in ("torch", "numpy"):
+            raise ValueError("io must be 'torch' or 'numpy'")
+        nat.require_cuda()
+        nat.lib()
+        self.env_id = env_id
+        self.kind = nat.KIND_OF_ID[env_id]
+        self.num_envs = int(num_envs)
+        self.io = io
+        self.cfg = normalise_kwargs(self.kind, env_kwargs)
+        self.auto_reset = bool(auto_reset)
+        self._seed = int(seed)
+        self.env_id_offset = int(env_id_offset)
+        self.observation_space = unit_box()
+        self.action_space = Discrete(self.cfg["n_actions"]) if self.kind == nat.V0 else unit_box()
+        self.metadata = {"render.modes": ["human"]}
+        self._pending = None
+        self._closed = False
+        self._handle = None
+        self.terminal_obs = None
+        if io == "torch":
+            self.batch = EnvBatch(self.kind, self.num_envs, device=device, env_id0=self.env_id_offset, seed=seed,
+                                  auto_reset=auto_reset, r=self.cfg["r"], K=self.cfg["K"], sigma=self.cfg["sigma"],
+                                  C=self.cfg["C"], x0=self.cfg["x0"], Tmax=self.cfg["Tmax"],
+                                  n_actions=self.cfg["n_actions"], sigma_p=self.cfg["sigma_p"])
+            self.device = self.batch.device
+            torch = self.batch.torch
+            self._reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            self._done = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.terminal_obs = torch.full((self.num_envs,), float("nan"), dtype=torch.float64, device=self.device)
+        else:
+            import torch
+
+            dev = torch.device(device)
+            self.device = dev
+            self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+            self._create_handle()
+
+    # ------------------------------------------------------------------------------------------------ numpy mode
+    def _params(self):
+        c = self.cfg
+        return nat.make_params(self.kind, r=c["r"], K=c["K"], sigma=c["sigma"], C_=c["C"], x0=c["x0"], Tmax=c["Tmax"],
+                               n_actions=c["n_actions"], sigma_p=c["sigma_p"], seed=self._seed,
+                               flags=nat.AUTO_RESET if self.auto_reset else 0)
+
+    def _create_handle(self):
+        h = ct.c_void_p()
+        p = self._params()
+        nat.check(nat.lib().fishing_vec_create(ct.byref(p), self.num_envs, self.env_id_offset, self._dev_index,
+                                               ct.byref(h)), "fishing_vec_create")
+        self._handle = h
+        n = self.num_envs
+        self._h_obs = _PinnedArray(n, np.float64)
+        self._h_reward = _PinnedArray(n, np.float64)
+        self._h_done = _PinnedArray(n, np.uint8)
+        self._h_term = _PinnedArray(n, np.float64)
+        self._h_act = _PinnedArray(n, np.float64)  # staging for pageable / wrongly-typed actions (8 bytes per env)
+
+    # ------------------------------------------------------------------------------------------------ VecEnv API
+    def reset(self):
+        """-> observations [num_envs, 1] float64 (BaseFishingEnv.reset, base_fishing_env.py:83-91; v4 redraws K, r)."""
+        self._check_open()
+        if self.io == "torch":
+            s = self.batch.reset()
+            return s.view(self.num_envs, 1)
+        nat.check(nat.lib().fishing_vec_reset(self._handle, self._h_obs.array.ctypes.data), "fishing_vec_reset")
+        return self._h_obs.array.reshape(self.num_envs, 1)
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        actions, self._pending = self._pending, None
+        if actions is None:
+            raise RuntimeError("step_wait() without step_async()")
+        return self._step(actions)
+
+    def step(self, actions):
+        """-> (obs [n,1] float64, rewards [n] float64, dones [n] bool, infos)  -- BaseFishingEnv.step
+        (base_fishing_env.py:60-81) for every environment, with SB3-style auto-reset when enabled."""
+        return self._step(actions)
+
+    def _step(self, actions):
+        self._check_open()
+        if self.io == "torch":
+            return self._step_torch(actions)
+        return self._step_numpy(actions)
+
+    def _coerce_torch_actions(self, actions):
+        torch = self.batch.torch
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        actions = actions.reshape(self.num_envs)
+        if self.kind == nat.V0:
+            if actions.dtype not in (torch.int32, torch.int64):
+                actions = actions.to(torch.int64)
+        elif actions.dtype not in (torch.float64, torch.float32):
+            actions = actions.to(torch.float64)
+        return actions.contiguous()
+
+    def _step_torch(self, actions):
+        b = self.batch
+        a = self._coerce_torch_actions(actions)
+        obs, rew, done = b.step(a, out_reward=self._reward, out_done=self._done,
+                                out_terminal=self.terminal_obs if self.auto_reset else None)
+        return obs.view(self.num_envs, 1), rew, done.view(b.torch.bool), LazyInfos(done, self.terminal_obs)
+
+    def step_into(self, actions, out_obs, out_reward, out_done, out_terminal=None, noise=None):
+        """torch mode, rollout-buffer form: write this step's observations / rewards / dones straight into the given
+        (contiguous, 1-D, length num_envs) slices, e.g. buf_obs[t], buf_reward[t], buf_done[t].  No allocation, no
+        copy: the observation slice becomes the engine's state for the next step."""
+        self._check_open()
+        a = self._coerce_torch_actions(actions)
+        self.batch.step(a, noise=noise, out_obs=out_obs.view(-1), out_reward=out_reward.view(-1),
+                        out_done=out_done.view(-1), out_terminal=out_terminal)
+
+    def _step_numpy(self, actions):
+        n = self.num_envs
+        a = np.asarray(actions)
+        if self.kind == nat.V0:
+            if a.dtype == np.int32:
+                adt = nat.ACT_I32
+            else:
+                a = a.astype(np.int64, copy=False)
+                adt = nat.ACT_I64
+        else:
+            if a.dtype == np.float32:
+                adt = nat.ACT_F32
+            else:
+                a = a.astype(np.float64, copy=False)
+                adt = nat.ACT_F64
+        a = np.ascontiguousarray(a.reshape(n))
+        rc = nat.lib().fishing_vec_step(self._handle, a.ctypes.data, adt, None, self._h_obs.array.ctypes.data,
+                                        self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data,
+                                        self._h_term.array.ctypes.data if self.auto_reset else None)
+        nat.check(rc, "fishing_vec_step")
+        done = self._h_done.array.view(np.bool_)
+        return (self._h_obs.array.reshape(n, 1), self._h_reward.array, done,
+                LazyInfos(done, self._h_term.array if self.auto_reset else None))
+
+    # ------------------------------------------------------------------------------------------------ attributes
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    def get_attr(self, attr_name, indices=None):
+        """list of per-env values (shared_env.py:73 calls env.get_attr("Tmax")[0])."""
+        idx = self._indices(indices)
+        c = self.cfg
+        shared = {"Tmax": c["Tmax"], "sigma": c["sigma"], "init_state": c["x0"], "n_actions": c["n_actions"], "C": c["C"],
+                  "sigma_p": c["sigma_p"], "K_mean": c["K"], "r_mean": c["r"]}
+        if attr_name in shared:
+            return [shared[attr_name] for _ in idx]
+        if attr_name in ("K", "r"):
+            if self.kind == nat.V4 and self.io == "torch":
+                t = (self.batch.K_env if attr_name == "K" else self.batch.r_env).cpu().numpy()
+                return [float(t[i]) for i in idx]
+            if self.kind == nat.V4:
+                raise NotImplementedError("per-env K/r are device resident; use io='torch' to read them")
+            return [c[attr_name] for _ in idx]
+        if attr_name in ("state", "years_passed") and self.io == "torch":
+            t = (self.batch.state if attr_name == "state" else self.batch.years).cpu().numpy()
+            return [np.array([t[i]]) if attr_name == "state" else int(t[i]) for i in idx]
+        raise AttributeError(attr_name)
+
+    def set_attr(self, attr_name, value, indices=None):
+        if indices is not None:
+            raise NotImplementedError("parameters are shared by the whole batch (except fishing-v4's drawn K, r)")
+        key = {"init_state": "x0", "K_mean": "K", "r_mean": "r"}.get(attr_name, attr_name)
+        if key not in self.cfg:
+            raise AttributeError(attr_name)
+        self.cfg[key] = value
+        if self.io == "torch":
+            self.batch.cfg["C_" if key == "C" else key] = value
+        else:
+            raise NotImplementedError("set_attr after construction needs io='torch'")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        """Only the pure unit conversions make sense on a batch (shared_env.py:17-19 calls get_fish_population)."""
+        idx = self._indices(indices)
+        K = self.get_attr("K", idx)
+        n_act = self.cfg["n_actions"]
+        out = []
+        for j, _ in enumerate(idx):
+            if method_name == "get_fish_population":
+                out.append(np.array([(np.asarray(method_args[0], dtype=np.float64).reshape(-1)[0] + 1) * K[j]]))
+            elif method_name == "get_state":
+                out.append(np.array([method_args[0] / K[j] - 1]))
+            elif method_name == "get_quota":
+                a = method_args[0]
+                out.append((a / n_act) * K[j] if self.kind == nat.V0 else
+                           (float(np.clip(np.asarray(a, dtype=np.float64).reshape(-1)[0], -1, 1)) + 1) * K[j])
+            elif method_name == "get_action":
+                q = method_args[0]
+                out.append(round(q * n_act / K[j]) if self.kind == nat.V0 else q / K[j] - 1)
+            else:
+                raise AttributeError(f"env_method({method_name!r}) is not available on the batched environment")
+        return out
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def seed(self, seed=None):
+        """Re-key the Philox noise streams (the reference has no seed(), base_fishing_env.py:13)."""
+        self._seed = 0 if seed is None else int(seed)
+        if self.io == "torch":
+            self.batch.cfg["seed"] = self._seed
+        else:
+            self.close()
+            self._closed = False
+            self._create_handle()
+        return [self._seed + i for i in range(min(self.num_envs, 8))]
+
+    def render(self, mode="human"):
+        raise NotImplementedError("render() logs one CSV row per step of ONE environment; use make(id) for that")
+
+    def _check_open(self):
+        if self._closed:
+            raise RuntimeError("environment is closed")
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        if self._handle is not None:
+            nat.lib().fishing_vec_destroy(self._handle)
+            self._handle = None
+            for a in (self._h_obs, self._h_reward, self._h_done, self._h_term, self._h_act):
+                a.free()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

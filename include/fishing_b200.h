@@ -1,0 +1,230 @@
+/*
+ * fishing_b200.h -- C ABI of the B200-native batched rollout engine for gym_fishing (fishing-v0/v1/v2/v4).
+ *
+ * The reference (boettiger-lab/gym_fishing) is pure Python and has no FFI; these entry points are what a
+ * ctypes binding on the reference side would call in place of the per-environment Python methods cited next
+ * to each function (reference paths are relative to the gym_fishing repository root).  INTEGRATION.md shows
+ * that binding.  Plain pointers and sizes only -- no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FISHING_E_* code for a bad argument, or a positive
+ *     cudaError_t; fishing_error_string() describes any of them.  Nothing is allocated or freed behind the
+ *     caller's back by the device-pointer entry points; they enqueue work on `stream` (a cudaStream_t passed
+ *     as void*, NULL = legacy default stream) and return without synchronising.
+ *   - "state" is the reference's normalised observation s = x/K - 1 (float64).  All arrays are
+ *     structure-of-arrays over environments.  Vectorised (16-byte) access is used when every pointer is
+ *     16-byte aligned and env_id0 and n are even; otherwise a scalar path computes identical results.
+ *   - arithmetic is IEEE-754 binary64, one rounding per reference operation, never contracted to FMA, so
+ *     results are bit-identical to the reference for v0/v1/v4 and within 1 ulp of libm `exp` for v2.
+ *   - noise: if `noise` is non-NULL it supplies the standard-normal draw of every environment for this step
+ *     (the reference's np.random.normal(0,1), base_fishing_env.py:130); otherwise the engine generates it from
+ *     a counter-based Philox4x32-10 stream keyed by (seed; env_id>>1, step_idx) + Box-Muller, so results do
+ *     not depend on how environments are partitioned over GPUs.  fishing_noise_fill() exports exactly those
+ *     draws so that they can be injected into the reference for parity checks.
+ */
+#ifndef FISHING_B200_H
+#define FISHING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FISHING_ABI_VERSION 1
+
+/* environment ids, gym_fishing/envs/__init__.py:17-35 */
+enum fishing_kind {
+  FISHING_V0 = 0, /* FishingEnv, discrete actions         gym_fishing/envs/fishing_env.py:6-24        */
+  FISHING_V1 = 1, /* FishingCtsEnv, Box actions           gym_fishing/envs/fishing_cts_env.py:4-12    */
+  FISHING_V2 = 2, /* FishingTippingEnv                    gym_fishing/envs/fishing_tipping_env.py:6-35 */
+  FISHING_V4 = 4  /* FishingModelError, per-env r and K   gym_fishing/envs/fishing_model_error.py:6-48 */
+};
+
+enum fishing_action_dtype {
+  FISHING_ACT_F64 = 0, /* Box action as float64 (the parity path)                                         */
+  FISHING_ACT_F32 = 1, /* Box action as float32: quota computed in float32 like numpy>=2 does (NEP 50)    */
+  FISHING_ACT_I32 = 2, /* Discrete action as int32                                                        */
+  FISHING_ACT_I64 = 3  /* Discrete action as int64 (what stable-baselines3 hands over)                    */
+};
+
+enum fishing_flags {
+  FISHING_AUTO_RESET = 1u << 0, /* stable-baselines3 VecEnv semantics: reset an env in the step that ends it */
+  FISHING_FREEZE_DONE = 1u << 1 /* rollout only: stop stepping an env after its first done                 */
+};
+
+enum fishing_policy {
+  FISHING_POLICY_ACTIONS = 0,    /* caller-supplied action tensor [T, n]                                   */
+  FISHING_POLICY_ESCAPEMENT = 1, /* escapement.predict, gym_fishing/models/policies.py:27-31               */
+  FISHING_POLICY_MSY = 2         /* msy.predict (constant quota), gym_fishing/models/policies.py:16-19     */
+};
+
+enum fishing_noise_stream {
+  FISHING_STREAM_STEP = 0,       /* process noise z of step t: ctr = (env>>1, t), lane = env&1              */
+  FISHING_STREAM_AUTORESET = 1,  /* v4 (zK, zr) of the auto-reset fired by step t: ctr = (env, t)           */
+  FISHING_STREAM_RESET = 2       /* v4 (zK, zr) of an explicit reset number `epoch`: ctr = (env, epoch)     */
+};
+
+enum fishing_error {
+  FISHING_E_ARG = -1,      /* NULL / negative size / unknown enum                       */
+  FISHING_E_KIND = -2,     /* action dtype or policy not valid for this environment id  */
+  FISHING_E_ALIGN = -3,    /* pointer not aligned to its element size                   */
+  FISHING_E_NODEVICE = -4, /* no CUDA device / not an sm_100 device                     */
+  FISHING_E_STATE = -5     /* handle used before reset, or already destroyed            */
+};
+
+/* Constructor keyword arguments of the reference classes (SURVEY.md section 5 "Config"):
+ * fishing_env.py:7-16, fishing_cts_env.py:5-7, fishing_tipping_env.py:7-16, fishing_model_error.py:9-19. */
+typedef struct fishing_params {
+  int32_t kind;      /* enum fishing_kind */
+  int32_t n_actions; /* v0 only (default 100) */
+  int32_t Tmax;      /* done = years_passed > Tmax (strict), base_fishing_env.py:76 */
+  uint32_t flags;    /* enum fishing_flags */
+  double r;          /* v4: r_mean */
+  double K;          /* v4: K_mean */
+  double sigma;
+  double C;          /* v2 only */
+  double x0;         /* init_state */
+  double sigma_p;    /* v4 only */
+  uint64_t seed;     /* Philox key */
+} fishing_params;
+
+/* Structure-of-arrays environment state (device pointers for the functions below). */
+typedef struct fishing_soa {
+  double* state;  /* [n] normalised state s; v4 straight after a reset holds x0 un-normalised (upstream quirk,
+                     fishing_model_error.py:44) */
+  int32_t* years; /* [n] years_passed */
+  double* K_env;  /* [n] v4 only, else NULL */
+  double* r_env;  /* [n] v4 only, else NULL */
+} fishing_soa;
+
+int fishing_abi_version(void);
+const char* fishing_error_string(int code);
+
+/* Number of kernel launches issued through this library since it was loaded (all entry points). */
+uint64_t fishing_launch_count(void);
+
+/*
+ * reset -- BaseFishingEnv.reset (base_fishing_env.py:83-91), FishingModelError.reset / __init__ draws
+ * (fishing_model_error.py:35-48).  `mask` (uint8[n], NULL = all) selects environments.  v4 draws K then r per
+ * env from reset_noise[0..n) and reset_noise[n..2n) when given, else from Philox stream FISHING_STREAM_RESET
+ * at counter `epoch`.  Writes soa.* and, if non-NULL, out_obs[n].
+ */
+int fishing_reset(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                  const double* reset_noise, fishing_soa soa, double* out_obs, void* stream);
+
+/*
+ * step -- BaseFishingEnv.step (base_fishing_env.py:60-81) with get_quota (:135-147), get_fish_population
+ * (:158-160), harvest_draw (:112-119), population_draw (:121-133; v2: fishing_tipping_env.py:24-35) and
+ * get_state (:162-164) fused, for n environments in lock-step.
+ *   action       [n] of `action_dtype`
+ *   noise        [n] standard normals or NULL (see header comment)
+ *   reset_noise  [2n] (zK then zr) for v4 auto-resets or NULL (Philox stream FISHING_STREAM_AUTORESET)
+ *   out_obs      [n] next observation (after auto-reset if that fired); may alias soa.state
+ *   out_reward   [n] max(harvest, 0)
+ *   out_done     [n] uint8, years_passed > Tmax or stock <= 0
+ *   out_terminal [n] or NULL: observation that ended the episode, written only where done (auto-reset mode)
+ *   out_stock    [n] or NULL: fish_population after growth (the attribute the reference leaves on the env)
+ *   out_harvest  [n] or NULL: harvest = min(stock, quota) before the max(., 0) of the reward
+ * step_idx is the global lock-step counter t (it keys the Philox stream); env_id0 the global id of element 0.
+ */
+int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                 int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa,
+                 double* out_obs, double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock,
+                 double* out_harvest, void* stream);
+
+/*
+ * noise_fill -- exports the engine's own draws: out[t*n + i] = z(env_id0 + i, step0 + t) for stream STEP, or
+ * out[(t*2 + j)*n + i] = (zK, zr)[j] for the v4 streams.  Same device code as used inside step / rollout.
+ */
+int fishing_noise_fill(uint64_t seed, int32_t noise_stream, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                       double* out, void* stream);
+
+/*
+ * rollout -- T fused steps with the state held in registers: the loop of simulate_mdp (shared_env.py:29-54)
+ * with the policy applied in-kernel.
+ *   policy        enum fishing_policy; ESCAPEMENT uses S (float32-valued BMSY result widened to double, or
+ *                 S_env[n] if non-NULL, e.g. an escapement sweep); MSY uses the constant quota msy_q
+ *   actions       [T, n] for FISHING_POLICY_ACTIONS (dtype action_dtype), else NULL
+ *   noise         [T, n] or NULL (Philox)
+ *   noise_id_div  0/1: noise keyed by env id; m > 1: env id / m is the noise id (common random numbers
+ *                 across the m policy levels of a sweep, SURVEY.md section 8d cfg 5)
+ *   out_return    [n] sum of rewards up to and including the first done step (sequential float64 adds)
+ *   out_done_step [n] int32 first t (0-based, relative to this call) with done, -1 if none
+ *   trace_*       [T, n] optional per-step outputs (NULL to skip)
+ * soa is read at entry and written back at exit (final state, years, K/r).  With FISHING_AUTO_RESET the
+ * environments restart inside the kernel and out_return accumulates over all episodes; with
+ * FISHING_FREEZE_DONE an environment stops at its first done (what simulate_mdp's `break` does).
+ */
+typedef struct fishing_rollout_args {
+  int32_t policy;
+  int32_t action_dtype;
+  int64_t T;
+  uint64_t step0;
+  double S;
+  const double* S_env;
+  double msy_q;
+  const void* actions;
+  const double* noise;
+  int64_t noise_id_div;
+  double* out_return;
+  int32_t* out_done_step;
+  double* trace_obs;
+  double* trace_reward;
+  uint8_t* trace_done;
+  double* trace_action;
+} fishing_rollout_args;
+
+int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const fishing_rollout_args* a,
+                    fishing_soa soa, void* stream);
+
+/*
+ * reduce_stats -- fixed-shape (pairwise tree, no atomics) reduction of per-env returns to
+ * out[g*3 + {0,1,2}] = {sum ret, sum ret^2, number with done_step >= 0} for `groups` interleaved groups:
+ * element i belongs to group i % groups (groups = 1: everything; groups = 1024: the levels of a sweep laid
+ * out [replicate, level]).  scratch must hold fishing_reduce_scratch_bytes(n, groups) bytes.
+ */
+int64_t fishing_reduce_scratch_bytes(int64_t n, int64_t groups);
+int fishing_reduce_stats(const double* ret, const int32_t* done_step, int64_t n, int64_t groups, void* scratch,
+                         double* out, void* stream);
+
+/*
+ * bmsy -- BMSY (gym_fishing/models/policies.py:51-67): argmax of deterministic growth over the 10001-point
+ * float32 grid on [0, 2K] (float64 grid when K_is_f64, the fishing-v4 case).  Synchronous; writes S and
+ * f(S) - S (the msy quota, policies.py:12) to host memory.
+ */
+int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out);
+
+/*
+ * population_draw -- BaseFishingEnv.population_draw (base_fishing_env.py:121-133; v2: fishing_tipping_env.py:24-35)
+ * on an array of stocks with ONE scalar draw z for the whole array, the way the reference's own callers use it
+ * (BMSY / msy, policies.py:9-14,60-65).  x and out are device arrays of float32 (is_f32 != 0: every operation is a
+ * float32 operation, numpy's result for a float32 array and Python-number parameters) or float64.
+ */
+int fishing_population_draw(const fishing_params* p, int64_t n, const void* x, int32_t is_f32, double z, void* out,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-buffer front end: the engine owns device state; the caller passes ordinary host arrays (numpy, pinned
+ * or pageable).  This is the entry a reference-side VecEnv binding uses and what bench.py's
+ * `e2e` figure times.  Copies are chunked and pipelined over three streams.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct fishing_vec fishing_vec;
+
+int fishing_vec_create(const fishing_params* p, int64_t n, int64_t env_id0, int32_t device, fishing_vec** out);
+int fishing_vec_destroy(fishing_vec* v);
+/* reset all environments; obs_out[n] host */
+int fishing_vec_reset(fishing_vec* v, double* obs_out);
+/* one lock-step; all pointers host; terminal_out may be NULL */
+int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, const double* noise, double* obs_out,
+                     double* reward_out, uint8_t* done_out, double* terminal_out);
+/* page-locked host memory helpers so that callers can make their numpy buffers DMA-able */
+int fishing_host_alloc(void** ptr, int64_t bytes);
+int fishing_host_free(void* ptr);
+/* device pointers of the handle's SoA state, for inspection */
+int fishing_vec_soa(fishing_vec* v, fishing_soa* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISHING_B200_H */

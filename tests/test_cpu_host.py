@@ -1,0 +1,166 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header declares, the
+package refuses to compute without a GPU (no silent fallback), spaces / registry / kwargs mapping, lazy infos, and
+the sharding + deterministic statistics combine under a 2-process gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "fishing_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fishing_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gym_fishing_b200 import _native as nat
+
+    assert os.path.exists(nat.LIB_PATH), "run `python __graft_entry__.py build` first"
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/fishing_b200.h but not exported"
+    assert sorted(nat.EXPORTS) == names
+    assert nat.lib().fishing_abi_version() == 1
+    assert b"bad argument" in nat.lib().fishing_error_string(-1)
+
+
+def test_struct_layouts_match_header_sizes():
+    from gym_fishing_b200 import _native as nat
+
+    assert ctypes.sizeof(nat.FishingParams) == 4 * 4 + 6 * 8 + 8
+    assert ctypes.sizeof(nat.FishingSoA) == 32
+    assert ctypes.sizeof(nat.FishingRolloutArgs) == 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 6 * 8
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gf.make("fishing-v1")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gf.FishingVecEnv("fishing-v1", num_envs=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gf.bmsy(1, r=0.3, K=1.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym_fishing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_registry_and_spaces():
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.spaces import Discrete, unit_box
+
+    assert gf.spec_ids() == ["fishing-v0", "fishing-v1", "fishing-v2", "fishing-v4"]
+    with pytest.raises(KeyError):
+        gf.make("fishing-v3")
+    b = unit_box()
+    assert b.low.dtype == np.float32 and b.low[0] == -1 and b.high[0] == 1 and b.shape == (1,)
+    assert b.contains(np.array([0.5], dtype=np.float32)) and not b.contains(np.array([1.5], dtype=np.float32))
+    assert b.sample().shape == (1,)
+    d = Discrete(100)
+    assert d.n == 100 and d.contains(99) and not d.contains(100) and 0 <= d.sample() < 100
+
+
+def test_ctor_kwargs_mapping():
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.vec_env import normalise_kwargs
+
+    c = normalise_kwargs(nat.V0, dict(r=0.5, K=2, sigma=0.1, n_actions=7, init_state=0.3, Tmax=9, file=None))
+    assert (c["r"], c["K"], c["sigma"], c["n_actions"], c["x0"], c["Tmax"]) == (0.5, 2, 0.1, 7, 0.3, 9)
+    c = normalise_kwargs(nat.V4, dict(K_mean=2.0, r_mean=0.5, sigma_p=0.2, price=3.0))
+    assert (c["K"], c["r"], c["sigma_p"]) == (2.0, 0.5, 0.2)
+    with pytest.raises(TypeError):
+        normalise_kwargs(nat.V1, dict(C=0.3))
+    with pytest.raises(TypeError):
+        normalise_kwargs(nat.V2, dict(n_actions=3))
+
+
+def test_lazy_infos():
+    from gym_fishing_b200.vec_env import LazyInfos
+
+    done = np.array([0, 1, 0], dtype=bool)
+    term = np.array([np.nan, -0.25, np.nan])
+    infos = LazyInfos(done, term)
+    assert len(infos) == 3 and infos[0] == {} and infos[2] == {}
+    assert infos[1]["terminal_observation"].shape == (1,) and infos[1]["terminal_observation"][0] == -0.25
+    assert [bool(i) for i in infos] == [False, True, False]
+
+
+def test_shard_range_partitions_exactly():
+    from gym_fishing_b200.distributed import shard_range
+
+    for n, world, align in [(1 << 20, 8, 2), (1 << 24, 8, 2048), (10, 3, 2), (4096, 4, 2048), (6, 8, 2)]:
+        if n % align:
+            continue
+        spans = [shard_range(n, r, world, align) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a % align == 0 and b % align == 0
+    with pytest.raises(ValueError):
+        shard_range(7, 0, 2, 2)
+
+
+def test_tree_sum_is_the_aligned_subtree():
+    import torch
+
+    from gym_fishing_b200.distributed import tree_sum
+
+    rng = np.random.default_rng(0)
+    x = [torch.tensor(rng.standard_normal(5) * 10.0 ** rng.integers(-8, 8)) for _ in range(8)]
+    whole = tree_sum(x)
+    halves = tree_sum([tree_sum(x[:4]), tree_sum(x[4:])])
+    quarters = tree_sum([tree_sum(x[i:i + 2]) for i in range(0, 8, 2)])
+    assert torch.equal(whole, halves) and torch.equal(whole, quarters)
+
+
+GLOO_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from gym_fishing_b200.distributed import init_from_env, shard_range, allreduce_stats, barrier_max_ms, tree_sum
+rank, world, local = init_from_env(backend="gloo")
+assert world == 2 and dist.get_world_size() == 2
+lo, hi = shard_range(1 << 12, rank, world, align=2048)
+assert (lo, hi) == (rank * 2048, (rank + 1) * 2048)
+g = torch.Generator().manual_seed(7)
+full = torch.randn(2, 1024, 3, dtype=torch.float64, generator=g) * 1e3
+mine = full[rank].contiguous()
+det = allreduce_stats(mine, deterministic=True)
+assert torch.equal(det, tree_sum([full[0], full[1]]))
+plain = allreduce_stats(mine, deterministic=False)
+assert torch.allclose(plain, full.sum(0), rtol=1e-15, atol=0)
+assert barrier_max_ms(1.0 + rank) == 2.0
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_sharding_and_stats(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "ok 0" in res.stdout and "ok 1" in res.stdout
