@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the gym_fishing hot path on B200 (BASELINE.json's metric, configs[1]).
+
+Workload ("cfg2"): fishing-v1 (continuous quota), 2^20 environments per GPU in lock-step, r=0.3 K=1 sigma=0.01
+x0=0.75 Tmax=100, auto-reset on, float64 actions U(-1,1) from a pre-generated [T, n] tensor, Gaussian process noise
+generated in-kernel (Philox), observations / rewards / dones written into a [T, n] rollout buffer.  One bench "step"
+is ONE pass of T=1000 lock-steps over the batch = T * n env-steps, i.e. T launches of the single-step kernel K1
+(issued from C, replayed as a CUDA graph).  Inputs (8.4 GB of actions) and outputs (18 GB) are far larger than the
+126 MB L2, so consecutive bench steps cannot be served from cache.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port), all cores
+
+Multi-GPU: one process per GPU under torchrun; environments are independent ("replicas only" for the VecEnv
+workload), every rank steps its own 2^20-env shard of the global id range, the time is the max
+over ranks -> weak scaling.
+
+Prints ONE JSON line (rank 0).  Keys beyond the contract: roofline (dominant kernel = K1, HBM-bound), cpu_baseline,
+e2e (host numpy buffers through the C-ABI host front end, copies inside the timed region), fused (the register-resident
+K2 variants of the same workload, reported for context), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(r=0.3, K=1.0, sigma=0.01, x0=0.75, Tmax=100)
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+# algorithmic bytes per env-step of K1 in this mode: state in 8 + action in 8 + obs out 8 +
+# reward out 8 + done out 1 + years int32 read+write 8
+K1_BYTES = 41
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baselines
+def _port_worker(args):
+    """`steps` env.step calls of the reference-shaped scalar port (oracle/fishing_oracle.py:ScalarPortEnv)."""
+    steps, seed = args
+    import numpy as np
+
+    from oracle.fishing_oracle import ScalarPortEnv
+
+    np.random.seed(seed)
+    env = ScalarPortEnv("v1", r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
+    acts = np.random.uniform(-1, 1, size=(1024, 1))
+    env.reset()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, _, done, _ = env.step(acts[i & 1023])
+        if done:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+def cpu_port_throughput(steps_per_proc, procs):
+    if procs == 1:
+        dt = _port_worker((steps_per_proc, 0))
+        return steps_per_proc / dt
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_port_worker, [(1000, i) for i in range(procs)])  # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(_port_worker, [(steps_per_proc, i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    return steps_per_proc * procs / wall
+
+
+def cpu_vectorised_throughput(n=1 << 20, T=8):
+    """Best-effort CPU line: the numpy-vectorised oracle on the same batch shape (single thread)."""
+    import numpy as np
+
+    from oracle import fishing_oracle as fo
+
+    rng = np.random.default_rng(0)
+    s = np.full(n, CFG["x0"] / CFG["K"] - 1)
+    years = np.zeros(n, dtype=np.int64)
+    a = rng.uniform(-1, 1, size=(T, n))
+    z = rng.standard_normal((T, n))
+    t0 = time.perf_counter()
+    for t in range(T):
+        s, _, done, years = fo.step_vec("v1", s, a[t], z[t], years, r=CFG["r"], K=CFG["K"], sigma=CFG["sigma"], Tmax=CFG["Tmax"])
+        s = np.where(done, CFG["x0"] / CFG["K"] - 1, s)
+        years = np.where(done, 0, years)
+    return n * T / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
+    to the GPU box, so this times the oracle's reference-shaped scalar port (same numpy-scalar operations per step,
+    validated bit-for-bit against the reference in tests/test_oracle_golden.py) on every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_proc = args.ref_steps_per_core
+    vals = []
+    for _ in range(args.warmup):
+        cpu_port_throughput(max(1000, per_proc // 10), cores)
+    for _ in range(args.steps):
+        vals.append(cpu_port_throughput(per_proc, cores))
+    v = sum(vals) / len(vals)
+    sample = f"{per_proc} env.step calls per process x {cores} processes per bench step, fishing-v1 sigma=0.01, auto-reset on done"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_proc * cores / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "cfg2: fishing-v1, 2^20 envs/GPU lock-step, sigma=0.01, random-action tensor [T,n] f64, in-kernel Philox noise, "
+                        "auto-reset, rollout-buffer outputs",
+            "envs_per_gpu": args.envs, "T_lockstep_per_bench_step": args.T, "env": "fishing-v1", "sigma": CFG["sigma"],
+            "r": CFG["r"], "K": CFG["K"], "x0": CFG["x0"], "Tmax": CFG["Tmax"], "parallelism": f"replicas x{world}",
+            "l2": "inputs+outputs per bench step (26 GB) >> 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.distributed import barrier_max_ms, init_from_env
+    from gym_fishing_b200.engine import EnvBatch
+    from gym_fishing_b200.vec_env import FishingVecEnv
+
+    rank, world, local = init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+
+    n, T = args.envs, args.T
+    lib = nat.lib()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.rand((T, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    obs = torch.empty((T, n), dtype=torch.float64, device=dev)
+    rew = torch.empty((T, n), dtype=torch.float64, device=dev)
+    done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+    batch = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
+    batch.reset()
+
+    # capture T launches of K1 into one CUDA graph on a side stream (the kernels go to whatever stream is current)
+    stream = torch.cuda.Stream(device=dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        batch.step_many(actions, obs, rew, done)  # warm-up outside capture (module load etc.)
+        stream.synchronize()
+        l0 = lib.fishing_launch_count()
+        with torch.cuda.graph(graph, stream=stream):
+            batch.step_many(actions, obs, rew, done)
+        launches_per_step = lib.fishing_launch_count() - l0
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            graph.replay()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record(stream)
+            for _ in range(args.steps):
+                graph.replay()
+            e1.record(stream)
+            barrier()
+        ms = e0.elapsed_time(e1)
+    ms = barrier_max_ms(ms, dev)
+    value = world * n * T * args.steps / (ms * 1e-3)
+    k1_us = ms * 1e3 / (args.steps * launches_per_step)
+
+    # sanity: the timed work really happened (dones fire, rewards are finite and non-trivial)
+    frac_done = float(done[-1].float().mean().item())
+    mean_rew = float(rew[-1].mean().item())
+    assert 0.0 < frac_done < 1.0 and mean_rew > 0.0 and bool(torch.isfinite(obs[-1]).all())
+
+    # ---- fused variants of the same workload (context): K2 with the action tensor, trace on / off
+    fused = {}
+    with torch.cuda.stream(stream):
+        for name, kw in (("actions_tensor_with_trace", dict(trace=True)), ("actions_tensor_returns_only", dict())):
+            b2 = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
+            b2.reset()
+            b2.rollout(T, policy="actions", actions=actions, **kw)
+            stream.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            f0.record(stream)
+            for _ in range(reps):
+                out = b2.rollout(T, policy="actions", actions=actions, **kw)
+            f1.record(stream)
+            stream.synchronize()
+            fms = barrier_max_ms(f0.elapsed_time(f1) / reps, dev)
+            fused[name] = {"value": world * n * T / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms}
+            del out, b2
+        S = 0.49960005283355713  # float32 BMSY of the default logistic model (tests/golden/kat.json kat1.S)
+        b3 = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
+        b3.reset()
+        b3.rollout(T, policy="escapement", S=S)
+        stream.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(3):
+            b3.rollout(T, policy="escapement", S=S)
+        f1.record(stream)
+        stream.synchronize()
+        fms = barrier_max_ms(f0.elapsed_time(f1) / 3, dev)
+        fused["escapement_in_kernel"] = {"value": world * n * T / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms}
+    del obs, rew, done, b3
+    torch.cuda.empty_cache()
+
+    # ---- e2e: numpy host buffers through the C-ABI host front end (H2D of actions, D2H of obs/reward/done every lock-step)
+    e2e_T = min(T, args.e2e_T)
+    venv = FishingVecEnv("fishing-v1", num_envs=n, device=dev, io="numpy", seed=0, auto_reset=True, env_id_offset=rank * n,
+                         r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
+    venv.reset()
+    import numpy as np
+
+    from gym_fishing_b200.vec_env import _PinnedArray
+
+    pinned = _PinnedArray(n * 8, np.float64)
+    h_act = pinned.array.reshape(8, n)
+    h_act[:] = np.random.default_rng(rank).uniform(-1, 1, size=(8, n))
+    for t in range(3):
+        venv.step(h_act[t % 8])
+    barrier()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for t in range(e2e_T):
+        o, r_, d_, _ = venv.step(h_act[t % 8])
+        acc += float(r_[0])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = barrier_max_ms(e2e_ms, dev)
+    e2e_value = world * n * e2e_T / (e2e_ms * 1e-3)
+    venv.close()
+    pinned.free()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = K1_BYTES * n / (k1_us * 1e-6) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v1 = cpu_port_throughput(args.cpu_steps, 1)
+            cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{args.cpu_steps} env.step calls of the reference-shaped scalar port (oracle.ScalarPortEnv), fishing-v1 sigma=0.01",
+                   "numpy_vectorised_1core": cpu_vectorised_throughput()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "step_kernel_vec2<LOGISTIC,P_KONE,F64>", "bytes_per_env_step": K1_BYTES,
+                         "avg_launch_us": k1_us, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * e2e_T, "d2h_bytes_per_step": n * 17 * e2e_T,
+                    "lock_steps_timed": e2e_T, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step (pinned host buffers)"},
+            "fused": fused,
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks.summary(),
+            "check": {"frac_done_last_step": frac_done, "mean_reward_last_step": mean_rew},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--e2e-T", dest="e2e_T", type=int, default=200)
+    ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=1_000_000)
+    ap.add_argument("--ref-steps-per-core", dest="ref_steps_per_core", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

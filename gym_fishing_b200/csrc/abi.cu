@@ -139,6 +139,27 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
 }
 
+int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                      const void* actions, int32_t action_dtype, const double* noise, fishing_soa soa, double* out_obs,
+                      double* out_reward, uint8_t* out_done, double* out_terminal, void* stream) {
+  if (T < 0 || n < 0) return FISHING_E_ARG;
+  const int asz = act_size(action_dtype);
+  if (!asz) return FISHING_E_ARG;
+  fishing_soa cur = soa;
+  for (int64_t t = 0; t < T; ++t) {
+    const int64_t off = t * n;
+    int rc = fishing_step(p, n, env_id0, step0 + (uint64_t)t, static_cast<const char*>(actions) + off * asz, action_dtype,
+                          noise ? noise + off : nullptr, nullptr, cur, out_obs + off, out_reward + off, out_done + off,
+                          out_terminal ? out_terminal + off : nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    cur.state = out_obs + off;
+  }
+  if (T > 0 && n > 0 && cur.state != soa.state)
+    return (int)cudaMemcpyAsync(soa.state, cur.state, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                static_cast<cudaStream_t>(stream));
+  return 0;
+}
+
 int fishing_noise_fill(uint64_t seed, int32_t noise_stream, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
                        double* out, void* stream) {
   if (n < 0 || T < 0 || env_id0 < 0 || !out || noise_stream < 0 || noise_stream > 2) return FISHING_E_ARG;
@@ -350,7 +371,7 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
     if (s.K_env) { s.K_env += off; s.r_env += off; }
     rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, noise ? v->d_noise + off : nullptr,
                       nullptr, s, v->d_obs + off, v->d_reward + off, v->d_done + off,
-                      terminal_out ? v->d_terminal + off : nullptr, nullptr, nullptr, st);
+                      v->d_terminal + off, nullptr, nullptr, st);
     if (rc) break;
     e = cudaMemcpyAsync(obs_out + off, v->d_obs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(reward_out + off, v->d_reward + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
@@ -365,6 +386,15 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
   }
   v->step_idx += 1;
   return rc;
+}
+
+int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out) {
+  if (!v || !terminal_out) return FISHING_E_ARG;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(terminal_out, v->d_terminal, (size_t)v->n * sizeof(double), cudaMemcpyDeviceToHost, v->streams[0]);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(v->streams[0]);
 }
 
 int fishing_host_alloc(void** ptr, int64_t bytes) {

@@ -216,8 +216,31 @@ __global__ void __launch_bounds__(256) noise_fill_kernel(uint64_t seed, int32_t 
 // np.float64 scalars and the grid is promoted to float64.  One block; argmax keeps the FIRST maximum like np.argmax.
 template <typename F>
 __device__ __forceinline__ F f_exp(F v);
+// numpy's float32 exp (numpy/_core/src/umath/loops_exponent_log.dispatch.c.src, simd_exp_FLOAT; the AVX2+FMA3 and
+// AVX512F builds share it): Cody-Waite reduction by ln2 with FMAs, a (5,2) rational minimax P(r)/Q(r), scale by 2^n.
+// It is NOT correctly rounded (it differs from the rounded true value on ~40 % of inputs), and fishing-v2's BMSY is
+// an argmax over float32 values that tie to the last bit, so the reference's S = 0x1.9374bcp-1 is only reproduced by
+// reproducing this algorithm operation for operation.  tests/test_np_expf.py pins the restatement to np.exp itself.
+__device__ __forceinline__ float np_expf(float x) {
+  if (x != x) return x;
+  if (x > 88.72283935546875f) return INFINITY;
+  if (x < -103.97208404541015625f) return 0.0f;
+  const float magic = 12582912.0f;  // 0x1.8p23: add/subtract rounds to the nearest integer
+  float q = __fmul_rn(x, 1.442695040888963407359924681001892137f);
+  q = __fsub_rn(__fadd_rn(q, magic), magic);
+  float r = __fmaf_rn(q, -6.93145752e-1f, x);
+  r = __fmaf_rn(q, -1.42860677e-6f, r);
+  float num = __fmaf_rn(5.082762527590693718096e-04f, r, 6.757896990527504603057e-03f);
+  num = __fmaf_rn(num, r, 5.114512081637298353406e-02f);
+  num = __fmaf_rn(num, r, 2.473615434895520810817e-01f);
+  num = __fmaf_rn(num, r, 7.257664613233124478488e-01f);
+  num = __fmaf_rn(num, r, 9.999999999980870924916e-01f);
+  float den = __fmaf_rn(2.159509375685829852307e-02f, r, -2.742335390411667452936e-01f);
+  den = __fmaf_rn(den, r, 1.0f);
+  return ldexpf(__fdiv_rn(num, den), (int)q);
+}
 template <>
-__device__ __forceinline__ float f_exp<float>(float v) { return (float)exp((double)v); }
+__device__ __forceinline__ float f_exp<float>(float v) { return np_expf(v); }
 template <>
 __device__ __forceinline__ double f_exp<double>(double v) { return exp(v); }
 

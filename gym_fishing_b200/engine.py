@@ -143,6 +143,28 @@ class EnvBatch:
         self.state = out_obs  # the newest observations ARE the state (no copy)
         return out_obs, out_reward, out_done
 
+    def step_many(self, actions, out_obs, out_reward, out_done, *, noise=None, out_terminal=None):
+        """fishing_step_many: T = actions.shape[0] lock-steps into rollout buffers [T, n] (one launch per step, issued
+        from C; capturable in a CUDA graph).  self.state keeps its own storage and holds the final state."""
+        torch = self.torch
+        T = actions.shape[0]
+        _chk_dev(actions, "actions", None, T * self.n)
+        adt = _act_dtype(actions)
+        _chk_dev(out_obs, "out_obs", torch.float64, T * self.n)
+        _chk_dev(out_reward, "out_reward", torch.float64, T * self.n)
+        _chk_dev(out_done, "out_done", torch.uint8, T * self.n)
+        if noise is not None:
+            _chk_dev(noise, "noise", torch.float64, T * self.n)
+        if out_terminal is not None:
+            _chk_dev(out_terminal, "out_terminal", torch.float64, T * self.n)
+        p = self.params()
+        with torch.cuda.device(self.device):
+            rc = nat.lib().fishing_step_many(ct.byref(p), self.n, self.env_id0, self.step_idx, T, actions.data_ptr(), adt,
+                                             _ptr(noise), self.soa(), out_obs.data_ptr(), out_reward.data_ptr(),
+                                             out_done.data_ptr(), _ptr(out_terminal), _stream(self.device))
+        nat.check(rc, "fishing_step_many")
+        self.step_idx += T
+
     def noise(self, T, *, stream=nat.STREAM_STEP, step0=None):
         """fishing_noise_fill: the engine's own Philox/Box-Muller draws, [T, n] (or [T, 2, n] for the v4 streams)."""
         torch = self.torch

@@ -76,6 +76,23 @@ class LazyInfos:
         return (self[i] for i in range(len(self)))
 
 
+class _LazyTerminal:
+    """Terminal observations of the latest numpy-mode step, copied from the device the first time one is read."""
+
+    def __init__(self, env):
+        self._env, self._step, self._arr = env, env._steps_done + 1, None
+
+    def __getitem__(self, i):
+        if self._arr is None:
+            env = self._env
+            if env._steps_done != self._step:
+                raise RuntimeError("terminal observations must be read before the next step() call")
+            nat.check(nat.lib().fishing_vec_fetch_terminal(env._handle, env._h_term.array.ctypes.data),
+                      "fishing_vec_fetch_terminal")
+            self._arr = env._h_term.array
+        return self._arr[i]
+
+
 class _PinnedArray:
     """numpy view over page-locked host memory from fishing_host_alloc (freed with the owner)."""
 
@@ -115,6 +132,7 @@ class FishingVecEnv:
         self.action_space = Discrete(self.cfg["n_actions"]) if self.kind == nat.V0 else unit_box()
         self.metadata = {"render.modes": ["human"]}
         self._pending = None
+        self._steps_done = 0
         self._closed = False
         self._handle = None
         self.terminal_obs = None
@@ -233,12 +251,12 @@ class FishingVecEnv:
                 adt = nat.ACT_F64
         a = np.ascontiguousarray(a.reshape(n))
         rc = nat.lib().fishing_vec_step(self._handle, a.ctypes.data, adt, None, self._h_obs.array.ctypes.data,
-                                        self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data,
-                                        self._h_term.array.ctypes.data if self.auto_reset else None)
+                                        self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data, None)
         nat.check(rc, "fishing_vec_step")
+        self._steps_done += 1
         done = self._h_done.array.view(np.bool_)
         return (self._h_obs.array.reshape(n, 1), self._h_reward.array, done,
-                LazyInfos(done, self._h_term.array if self.auto_reset else None))
+                LazyInfos(done, _LazyTerminal(self) if self.auto_reset else None))
 
     # ------------------------------------------------------------------------------------------------ attributes
     def _indices(self, indices):

@@ -134,6 +134,17 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
                  double* out_harvest, void* stream);
 
 /*
+ * step_many -- T consecutive lock-steps into a caller-owned rollout buffer (what an on-policy collector fills):
+ * step t reads actions[t*n ..], writes out_obs / out_reward / out_done (/ out_terminal) at [t*n ..], and takes the
+ * observations of step t-1 as its state, so no separate state array is read or written between steps.  One kernel
+ * launch per step, issued back to back on `stream` (capturable into a CUDA graph); soa.state is updated with the
+ * final state at the end.  Identical results to T calls of fishing_step with step_idx = step0 + t.
+ */
+int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
+                      const void* actions, int32_t action_dtype, const double* noise, fishing_soa soa, double* out_obs,
+                      double* out_reward, uint8_t* out_done, double* out_terminal, void* stream);
+
+/*
  * noise_fill -- exports the engine's own draws: out[t*n + i] = z(env_id0 + i, step0 + t) for stream STEP, or
  * out[(t*2 + j)*n + i] = (zK, zr)[j] for the v4 streams.  Same device code as used inside step / rollout.
  */
@@ -221,6 +232,9 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
 /* page-locked host memory helpers so that callers can make their numpy buffers DMA-able */
 int fishing_host_alloc(void** ptr, int64_t bytes);
 int fishing_host_free(void* ptr);
+/* terminal observations of the most recent step (valid where that step reported done), fetched on demand so that the
+ * per-step device-to-host traffic stays at obs + reward + done */
+int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out);
 /* device pointers of the handle's SoA state, for inspection */
 int fishing_vec_soa(fishing_vec* v, fishing_soa* out);
 

@@ -25,15 +25,19 @@ def _torch():
     return torch
 
 
-def same(a, b, kind, what=""):
+def same(a, b, kind, what="", scale=1.0):
+    """Bit-exact, except fishing-v2: |a - b| <= 1e-12 * max(|b|, scale) with scale = K, the size of the stock.  (A purely
+    relative bound cannot hold for v2: one ulp of `exp` in a stock x becomes a large RELATIVE error in x - quota when
+    the quota takes almost everything -- the same happens between two numpy builds of the reference itself.)"""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     if kind == "v2":
-        ok = np.allclose(a, b, rtol=RTOL_V2, atol=1e-300, equal_nan=True)
+        ok = np.allclose(a, b, rtol=RTOL_V2, atol=RTOL_V2 * scale, equal_nan=True)
     else:
         ok = np.array_equal(a, b, equal_nan=True)
     if not ok:
-        bad = np.flatnonzero(~np.isclose(a.ravel(), b.ravel(), rtol=0 if kind != "v2" else RTOL_V2, atol=0, equal_nan=True))
+        bad = np.flatnonzero(~np.isclose(a.ravel(), b.ravel(), rtol=0 if kind != "v2" else RTOL_V2,
+                                         atol=0 if kind != "v2" else RTOL_V2 * scale, equal_nan=True))
         raise AssertionError(f"{what}: {bad.size} mismatches, first at {bad[:5]}: {a.ravel()[bad[:5]]} vs {b.ravel()[bad[:5]]}")
 
 
@@ -71,8 +75,8 @@ def test_golden_trajectories_one_env_per_launch(kind):
         done = torch.empty(T, 1, dtype=torch.uint8, device="cuda")
         for t in range(T):
             b.step(acts[t], noise=noise[t], out_obs=obs[t], out_reward=rew[t], out_done=done[t])
-        same(obs.cpu().numpy()[:, 0], d["obs"][:, m], kind, f"{kind} traj {m} obs")
-        same(rew.cpu().numpy()[:, 0], d["reward"][:, m], kind, f"{kind} traj {m} reward")
+        same(obs.cpu().numpy()[:, 0], d["obs"][:, m], kind, f"{kind} traj {m} obs", 4.0)
+        same(rew.cpu().numpy()[:, 0], d["reward"][:, m], kind, f"{kind} traj {m} reward", 4.0)
         assert np.array_equal(done.cpu().numpy()[:, 0], d["done"][:, m]), (kind, m)
 
 
@@ -96,9 +100,9 @@ def test_golden_autoreset_trajectories(kind):
         for t in range(T):
             b.step(acts[t], noise=noise[t], reset_noise=rnoise[t + 1] if kind == "v4" else None, out_obs=obs[t],
                    out_reward=rew[t], out_done=done[t], out_terminal=term[t])
-        same(obs.cpu().numpy()[:, 0], d["obs"][:, m], kind, f"{kind} autoreset {m} obs")
-        same(rew.cpu().numpy()[:, 0], d["reward"][:, m], kind, f"{kind} autoreset {m} reward")
-        same(term.cpu().numpy()[:, 0], d["term"][:, m], kind, f"{kind} autoreset {m} terminal")
+        same(obs.cpu().numpy()[:, 0], d["obs"][:, m], kind, f"{kind} autoreset {m} obs", 4.0)
+        same(rew.cpu().numpy()[:, 0], d["reward"][:, m], kind, f"{kind} autoreset {m} reward", 4.0)
+        same(term.cpu().numpy()[:, 0], d["term"][:, m], kind, f"{kind} autoreset {m} terminal", 4.0)
         assert np.array_equal(done.cpu().numpy()[:, 0], d["done"][:, m])
         if kind == "v4":
             assert b.K_env.item() == d["K_env"][T, m] and b.r_env.item() == d["r_env"][T, m]
@@ -159,10 +163,10 @@ def test_batched_step_matches_oracle(kind, cfg, n, auto_reset):
         b.step(d_act[t], noise=d_noise[t], reset_noise=d_rn[t + 1] if kind == "v4" else None, out_obs=obs[t],
                out_reward=rew[t], out_done=done[t], out_terminal=term[t] if auto_reset else None)
     assert np.array_equal(done.cpu().numpy(), exp["done"]), "done flags must be bit-exact"
-    same(obs.cpu().numpy(), exp["obs"], kind, "obs")
-    same(rew.cpu().numpy(), exp["reward"], kind, "reward")
+    same(obs.cpu().numpy(), exp["obs"], kind, "obs", cfg["K"])
+    same(rew.cpu().numpy(), exp["reward"], kind, "reward", cfg["K"])
     if auto_reset:
-        same(term.cpu().numpy(), exp["term"], kind, "terminal obs")
+        same(term.cpu().numpy(), exp["term"], kind, "terminal obs", cfg["K"])
         assert exp["done"].sum() > 0
     assert np.array_equal(b.years.cpu().numpy(), exp["years"])
 
@@ -290,15 +294,15 @@ def test_fused_rollout_matches_oracle_and_single_steps(kind, cfg, policy):
                          n_actions=cfg.get("n_actions", 100), Tmax=cfg["Tmax"], policy=policy, actions=acts, S=S,
                          msy_q=msy_q, noise=noise)
     assert np.array_equal(out["done"].cpu().numpy(), exp["done"])
-    same(out["obs"].cpu().numpy(), exp["obs"], kind, "trace obs")
-    same(out["reward"].cpu().numpy(), exp["reward"], kind, "trace reward")
+    same(out["obs"].cpu().numpy(), exp["obs"], kind, "trace obs", cfg["K"])
+    same(out["reward"].cpu().numpy(), exp["reward"], kind, "trace reward", cfg["K"])
     if kind == "v0" or policy == "actions":
         assert np.array_equal(out["action"].cpu().numpy(), exp["action"].astype(np.float64), equal_nan=True)
     else:
-        same(out["action"].cpu().numpy(), exp["action"], kind, "trace action")
-    same(out["ret"].cpu().numpy(), exp["ret"], kind, "return")
+        same(out["action"].cpu().numpy(), exp["action"], kind, "trace action", cfg["K"])
+    same(out["ret"].cpu().numpy(), exp["ret"], kind, "return", cfg["K"] * T)
     assert np.array_equal(out["done_step"].cpu().numpy(), exp["done_step"])
-    same(b.state.cpu().numpy(), exp["final_state"], kind, "final state")
+    same(b.state.cpu().numpy(), exp["final_state"], kind, "final state", cfg["K"])
 
 
 def test_fused_rollout_with_philox_equals_T_single_steps_bitwise():
@@ -389,10 +393,7 @@ def test_bmsy_kernel_against_reference_table():
             S, _ = gf.bmsy(4, r=r, K=K, K_is_f64=True)
         else:
             S, q = gf.bmsy(KIND[kind], r=kw.get("r", 0.3), K=kw.get("K", 1), C=kw.get("C", 0.5))
-            if kind == "v2":
-                assert abs(q - fo.unhex(row["msy"])) <= 2e-7 * abs(q)
-            else:
-                assert float(q).hex() == row["msy"], row
+            assert float(q).hex() == row["msy"], row   # float32 arithmetic incl. numpy's float32 exp: exact
         assert float(S).hex() == row["S"], row
 
 
@@ -521,11 +522,8 @@ def test_scalar_policies_and_simulate_tables():
             pol = gf.msy(env)
             assert inj.i - row["draws_ctor"] == row["draws_msy"]
         assert float(pol.S).hex() == row["S"] and str(np.asarray(pol.S).dtype) == row["S_dtype"]
-        if kind == "v2":
-            assert abs(float(pol.msy) - fo.unhex(row["msy"])) <= 2e-7 * abs(float(pol.msy))
-        else:
-            assert float(pol.msy).hex() == row["msy"], row
-            assert float(pol.predict(np.array([0.0]))[0]).hex() == row["msy_action"]
+        assert float(pol.msy).hex() == row["msy"], row
+        assert float(pol.predict(np.array([0.0]))[0]).hex() == row["msy_action"]
     tabs = json.load(open(os.path.join(G, "simulate.json")))
     for tab in tabs:
         kind = "v" + tab["env"].split("-v")[1]
@@ -535,8 +533,6 @@ def test_scalar_policies_and_simulate_tables():
             df = env.simulate(pol, reps=tab["reps"])
         assert list(df.columns) == tab["columns"] and len(df) == len(tab["rows"])
         tol = 0.0 if kind != "v2" else 1e-12
-        if kind == "v2" and tab["policy"] == "msy":
-            tol = 1e-6  # msy itself is a float32 exp
         for mine, ref in zip(df.values.tolist(), tab["rows"]):
             assert int(mine[0]) == ref[0] and int(mine[4]) == ref[4]
             for j in (1, 2, 3):

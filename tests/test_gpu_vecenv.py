@@ -1,0 +1,169 @@
+"""FishingVecEnv (the new batched front end) on the GPU: SB3-VecEnv protocol, both I/O modes, rollout-buffer stepping,
+the reference's own VecEnv consumer, and size-independent properties at BASELINE.json's full batch size."""
+import numpy as np
+import pytest
+
+from oracle import fishing_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_protocol_shapes_dtypes_autoreset_and_terminal_observation():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n = 512
+    venv = gf.FishingVecEnv("fishing-v1", num_envs=n, sigma=0.0, Tmax=5)
+    assert venv.num_envs == n and venv.action_space.shape == (1,) and venv.observation_space.dtype == np.float32
+    obs = venv.reset()
+    assert obs.shape == (n, 1) and obs.dtype == torch.float64 and obs.is_cuda
+    assert torch.all(obs == -0.25)
+    act = torch.full((n, 1), -1.0, dtype=torch.float64, device="cuda")
+    act[::2] = 1.0  # even envs harvest everything -> extinct on the first step
+    obs, rew, done, infos = venv.step(act)
+    assert rew.shape == (n,) and done.shape == (n,) and done.dtype == torch.bool and len(infos) == n
+    assert bool(done[0]) and not bool(done[1])
+    assert float(obs[0, 0]) == -0.25, "auto-reset returns the reset observation"
+    assert infos[0]["terminal_observation"].shape == (1,) and float(infos[0]["terminal_observation"][0]) == -1.0
+    assert infos[1] == {}
+    assert float(rew[0]) == 0.75 and float(rew[1]) == 0.0
+    # time limit: done on step Tmax + 1 (strict '>' of base_fishing_env.py:76), counted per env since its own reset
+    act[:] = -1.0
+    dones = []
+    for t in range(6):
+        venv.step_async(act)
+        obs, rew, done, infos = venv.step_wait()
+        dones.append(done.cpu().numpy().copy())
+    dones = np.array(dones)
+    assert dones[:4].sum() == 0 and dones[4, 1::2].all() and not dones[4, ::2].any() and dones[5, ::2].all()
+    assert venv.get_attr("Tmax") == [5] * n and venv.get_attr("Tmax", indices=[0, 3]) == [5, 5]
+    assert venv.env_method("get_fish_population", (np.array([-0.25]),), indices=0)[0][0] == 0.75
+    assert venv.env_is_wrapped(object) == [False] * n
+    venv.close()
+    with pytest.raises(RuntimeError):
+        venv.step(act)
+
+
+def test_discrete_env_and_numpy_mode_equal_torch_mode():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 3000, 30
+    rng = np.random.default_rng(0)
+    for env_id, kw, mk in (("fishing-v0", dict(sigma=0.05, Tmax=10, n_actions=50), lambda: rng.integers(0, 12, size=n)),
+                           ("fishing-v1", dict(sigma=0.05, Tmax=10, K=2.0, init_state=1.2), lambda: rng.uniform(-1, -0.5, size=(n, 1))),
+                           ("fishing-v4", dict(sigma=0.02, Tmax=7), lambda: rng.uniform(-1, -0.5, size=(n, 1)).astype(np.float32))):
+        a = gf.FishingVecEnv(env_id, num_envs=n, io="torch", seed=3, **kw)
+        b = gf.FishingVecEnv(env_id, num_envs=n, io="numpy", seed=3, **kw)
+        oa, ob = a.reset(), b.reset()
+        assert isinstance(ob, np.ndarray) and ob.shape == (n, 1)
+        assert np.array_equal(oa.cpu().numpy(), ob)
+        ndone = 0
+        for t in range(T):
+            act = mk()
+            oa, ra, da, ia = a.step(torch.as_tensor(act, device="cuda"))
+            ob, rb, db, ib = b.step(act)
+            assert np.array_equal(oa.cpu().numpy(), ob) and np.array_equal(ra.cpu().numpy(), rb)
+            assert np.array_equal(da.cpu().numpy(), db) and db.dtype == np.bool_
+            idx = np.flatnonzero(db)
+            ndone += idx.size
+            if idx.size:
+                i = int(idx[0])
+                assert np.array_equal(ia[i]["terminal_observation"].cpu().numpy(), ib[i]["terminal_observation"])
+        assert ndone > n, "several episodes per env ended"
+        a.close()
+        b.close()
+
+
+def test_step_into_rollout_buffer_matches_oracle_with_exported_noise():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 4096, 64
+    venv = gf.FishingVecEnv("fishing-v1", num_envs=n, sigma=0.1, Tmax=20, seed=17)
+    venv.reset()
+    z = venv.batch.noise(T, step0=0).cpu().numpy()
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, -0.5, size=(T, n))
+    d_act = torch.as_tensor(acts, device="cuda")
+    obs = torch.empty(T, n, dtype=torch.float64, device="cuda")
+    rew = torch.empty_like(obs)
+    done = torch.empty(T, n, dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        venv.step_into(d_act[t], obs[t], rew[t], done[t])
+    exp = fo.rollout_vec("v1", T, n, r=0.3, K=1.0, sigma=0.1, x0=0.75, Tmax=20, policy="actions", actions=acts, noise=z,
+                         auto_reset=True)
+    assert np.array_equal(obs.cpu().numpy(), exp["obs"]) and np.array_equal(rew.cpu().numpy(), exp["reward"])
+    assert np.array_equal(done.cpu().numpy(), exp["done"]) and exp["done"].sum() > 0
+    # the C-side loop (fishing_step_many) gives the same buffers
+    venv2 = gf.FishingVecEnv("fishing-v1", num_envs=n, sigma=0.1, Tmax=20, seed=17)
+    venv2.reset()
+    obs2, rew2, done2 = torch.empty_like(obs), torch.empty_like(rew), torch.empty_like(done)
+    venv2.batch.step_many(d_act, obs2, rew2, done2)
+    assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(done, done2)
+    assert torch.equal(venv2.batch.state, obs2[-1])
+
+
+def test_reference_vecenv_consumer_simulate_mdp_vec():
+    """shared_env.py:57-79 run against the batched env (numpy mode) with a constant-action model."""
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.shared_env import simulate_mdp_vec
+
+    class Const:
+        def predict(self, obs, state=None, mask=None):
+            return np.full((len(obs), 1), -0.9), state
+
+    venv = gf.FishingVecEnv("fishing-v1", num_envs=8, io="numpy", sigma=0.0, Tmax=12, auto_reset=False)
+    df = simulate_mdp_vec(venv, Const(), 16)
+    assert list(df.columns) == ["time", "state", "action", "reward", "rep"] and len(df) == 2 * 13 * 8
+    one = df[df.rep == 11].sort_values("time")
+    exp = fo.rollout_vec("v1", 12, 1, r=0.3, K=1.0, sigma=0.0, x0=0.75, Tmax=12, policy="actions",
+                         actions=np.full((12, 1), -0.9))
+    assert np.array_equal(one.state.values[1:], (exp["obs"][:, 0] + 1) * 1.0)
+    assert np.array_equal(one.reward.values[1:], exp["reward"][:, 0])
+    venv.close()
+
+
+def test_full_size_properties_2pow20():
+    """At BASELINE.json's batch size the oracle is too slow to replay everything, so use properties that hold at any
+    size: (i) K1 x T == fused K2 bit for bit, (ii) two half shards with global ids == the whole batch, (iii) a random
+    sample of 4096 envs replayed through the oracle with the engine's exported noise."""
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.engine import EnvBatch
+
+    n, T = 1 << 20, 24
+    cfg = dict(r=0.3, K=1.0, sigma=0.01, x0=0.75, Tmax=100, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.rand((T, n), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    acts[:, ::3] = acts[:, ::3] * 0.1 - 0.9   # a third of the envs fish gently and survive
+    whole = EnvBatch(nat.V1, n, auto_reset=True, **cfg)
+    whole.reset()
+    obs = torch.empty(T, n, dtype=torch.float64, device="cuda")
+    rew = torch.empty_like(obs)
+    done = torch.empty(T, n, dtype=torch.uint8, device="cuda")
+    whole.step_many(acts, obs, rew, done)
+    fused = EnvBatch(nat.V1, n, auto_reset=True, **cfg)
+    fused.reset()
+    out = fused.rollout(T, policy="actions", actions=acts, trace=True)
+    assert torch.equal(out["obs"], obs) and torch.equal(out["reward"], rew) and torch.equal(out["done"], done)
+    half = n // 2
+    for lo in (0, half):
+        part = EnvBatch(nat.V1, half, env_id0=lo, auto_reset=True, **cfg)
+        part.reset()
+        o2 = torch.empty(T, half, dtype=torch.float64, device="cuda")
+        r2 = torch.empty_like(o2)
+        d2 = torch.empty(T, half, dtype=torch.uint8, device="cuda")
+        part.step_many(acts[:, lo:lo + half].contiguous(), o2, r2, d2)
+        assert torch.equal(o2, obs[:, lo:lo + half]) and torch.equal(d2, done[:, lo:lo + half])
+    idx = np.sort(np.random.default_rng(0).choice(n, 4096, replace=False))
+    z = whole.noise(T, step0=0)[:, idx].cpu().numpy()
+    exp = fo.rollout_vec("v1", T, idx.size, r=0.3, K=1.0, sigma=0.01, x0=0.75, Tmax=100, policy="actions",
+                         actions=acts[:, idx].cpu().numpy(), noise=z, auto_reset=True)
+    assert np.array_equal(obs[:, idx].cpu().numpy(), exp["obs"]) and np.array_equal(rew[:, idx].cpu().numpy(), exp["reward"])
+    assert np.array_equal(done[:, idx].cpu().numpy(), exp["done"])
+    assert 0.2 < exp["done"].mean() < 0.8
