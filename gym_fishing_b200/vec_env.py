@@ -80,7 +80,7 @@ class _LazyTerminal:
     """Terminal observations of the latest numpy-mode step, copied from the device the first time one is read."""
 
     def __init__(self, env):
-        self._env, self._step, self._arr = env, env._steps_done + 1, None
+        self._env, self._step, self._arr = env, env._steps_done, None
 
     def __getitem__(self, i):
         if self._arr is None:
