@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -54,6 +55,21 @@ static double reset_state_value(const fishing_params* p) {
   if (p->kind == FISHING_V4) return p->x0;
   volatile double q = p->x0 / p->K;
   return q - 1.0;
+}
+
+// FISHING_NO_PDL=1 in the environment switches programmatic dependent launch off (for A/B timing and debugging)
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("FISHING_NO_PDL");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  return on;
+}
+
+static bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
+  if (!a || !b) return false;
+  const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b);
+  return x < y + nb && y < x + na;
 }
 
 static int check_soa(const fishing_params* p, const fishing_soa& s) {
@@ -125,7 +141,7 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   a.s_reset = reset_state_value(p);
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
   a.n_actions = (double)p->n_actions;
-  a.Tmax = p->Tmax; a.flags = p->flags;
+  a.Tmax = p->Tmax; a.flags = p->flags & (FISHING_AUTO_RESET | FISHING_FREEZE_DONE);
   a.action = action; a.noise = noise; a.reset_noise = reset_noise;
   a.state_in = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
@@ -136,6 +152,8 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
              (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
              (!out_harvest || aligned(out_harvest, 16));
   if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
+  if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
+  if (vec && (p->flags & FISHING_PDL) && pdl_enabled()) a.flags |= STEP_FLAG_PDL;
   return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
 }
 
@@ -145,10 +163,22 @@ int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint6
   if (T < 0 || n < 0) return FISHING_E_ARG;
   const int asz = act_size(action_dtype);
   if (!asz) return FISHING_E_ARG;
+  // consecutive steps may overlap (PDL) when no step's inputs alias any step's outputs
+  const size_t tn = (size_t)T * (size_t)n;
+  fishing_params q = *p;
+  const void* ins[2] = {actions, noise};
+  const size_t in_bytes[2] = {tn * asz, tn * 8};
+  const void* outs[5] = {out_obs, out_reward, out_done, out_terminal, soa.state};
+  const size_t out_bytes[5] = {tn * 8, tn * 8, tn, tn * 8, (size_t)n * 8};
+  bool alias = false;
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 5; ++k) alias = alias || overlaps(ins[i], in_bytes[i], outs[k], out_bytes[k]);
+  if (alias) q.flags &= ~(uint32_t)FISHING_PDL;
+  else q.flags |= FISHING_PDL;
   fishing_soa cur = soa;
   for (int64_t t = 0; t < T; ++t) {
     const int64_t off = t * n;
-    int rc = fishing_step(p, n, env_id0, step0 + (uint64_t)t, static_cast<const char*>(actions) + off * asz, action_dtype,
+    int rc = fishing_step(&q, n, env_id0, step0 + (uint64_t)t, static_cast<const char*>(actions) + off * asz, action_dtype,
                           noise ? noise + off : nullptr, nullptr, cur, out_obs + off, out_reward + off, out_done + off,
                           out_terminal ? out_terminal + off : nullptr, nullptr, nullptr, stream);
     if (rc) return rc;

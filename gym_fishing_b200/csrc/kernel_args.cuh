@@ -5,6 +5,10 @@
 
 namespace fishing {
 
+// internal launch flag (upper bits of StepArgs::flags, never part of the public fishing_flags): use programmatic
+// dependent launch for this step
+constexpr uint32_t STEP_FLAG_PDL = 1u << 16;
+
 struct StepArgs {
   int64_t n;          // environments in this launch
   int64_t env_id0;    // global id of element 0 (keys the Philox stream)

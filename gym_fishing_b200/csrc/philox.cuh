@@ -13,6 +13,13 @@
 //
 // Process noise (stream 0) uses id = env_id >> 1 and hands z0 to the even and z1 to the odd environment of the
 // pair, so one Philox block + one Box-Muller serves two environments.
+//
+// The three transcendental pieces are written out here instead of calling libdevice's log / sqrt / sincospi: the
+// arguments are known to be normal numbers in (0, 1), (0, 73] and (0, 2), so the denormal / inf / NaN / exact-integer
+// paths of the general routines (about a third of their instructions) are dead weight in a kernel that is
+// instruction-issue bound.  Same classical algorithms (fdlibm's log and kernel sin/cos polynomials, Newton square root
+// from the hardware reciprocal-sqrt seed), < 1.5 ulp each; tests/test_gpu_parity.py checks the draws against an
+// 80-bit long-double evaluation of the formulas above.
 #pragma once
 #include <stdint.h>
 
@@ -49,18 +56,113 @@ __device__ __forceinline__ double u52_to_open_unit(uint32_t lo, uint32_t hi) {
   return __dsub_rn(d, 0x1.fffffffffffffp-1);
 }
 
+__device__ __forceinline__ double rcp_seed(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+// Every operation below is an explicit round-to-nearest intrinsic, so the compiler has no contraction freedom and the
+// three kernels that inline this code (K1, K2, noise export) produce identical bits.
+#define FD_MUL(a, b) __dmul_rn((a), (b))
+#define FD_ADD(a, b) __dadd_rn((a), (b))
+#define FD_SUB(a, b) __dsub_rn((a), (b))
+#define FD_FMA(a, b, c) __fma_rn((a), (b), (c))
+
+// ln(u) for a NORMAL double 0 < u < 1 (fdlibm e_log.c algorithm: u = 2^e * m, m in [sqrt(1/2), sqrt(2)),
+// s = (m-1)/(m+1), log(m) = f - s*(f - R(s^2)), f = m - 1).
+__device__ __forceinline__ double log_unit(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000FFFFF) | 0x3FF00000;
+  if (hi >= 0x3FF6A09F) {  // m >= sqrt(2) (to the precision of the high word): halve it
+    hi -= 0x00100000;
+    e += 1;
+  }
+  const double m = __hiloint2double(hi, lo);
+  const double f = FD_SUB(m, 1.0);
+  const double g = FD_ADD(m, 1.0);
+  double rg = rcp_seed(g);                      // ~2^-20 relative
+  double t = FD_FMA(-g, rg, 1.0);
+  t = FD_FMA(t, t, t);
+  rg = FD_FMA(rg, t, rg);                       // ~2^-60
+  double s = FD_MUL(f, rg);
+  s = FD_FMA(FD_FMA(-s, g, f), rg, s);          // one correction step: s = f/g to < 1 ulp
+  const double z = FD_MUL(s, s);
+  double R = 1.479819860511658591e-01;
+  R = FD_FMA(R, z, 1.531383769920937332e-01);
+  R = FD_FMA(R, z, 1.818357216161805012e-01);
+  R = FD_FMA(R, z, 2.222219843214978396e-01);
+  R = FD_FMA(R, z, 2.857142874366239149e-01);
+  R = FD_FMA(R, z, 3.999999999940941908e-01);
+  R = FD_FMA(R, z, 6.666666666666735130e-01);
+  R = FD_MUL(R, z);
+  const double lm = FD_FMA(-s, FD_SUB(f, R), f);  // log(m)
+  // e as a double without a conversion instruction: the double with bits 0x43300000:(e xor 2^31) is 2^52 + 2^31 + e
+  const double ed = FD_SUB(__hiloint2double(0x43300000, e ^ 0x80000000), 4503601774854144.0);
+  return FD_FMA(ed, 6.93147180369123816490e-01, FD_FMA(ed, 1.90821492927058770002e-10, lm));
+}
+
+// sqrt(a) for a normal double a > 0 (no range checks): Newton on the hardware reciprocal-sqrt seed.
+__device__ __forceinline__ double sqrt_pos(double a) {
+  double y = rsqrt_seed(a);                     // ~2^-20
+  const double e = FD_FMA(FD_MUL(-a, y), y, 1.0);
+  y = FD_FMA(FD_MUL(y, FD_FMA(e, 0.375, 0.5)), e, y);  // y ~ a^-1/2 to ~2^-56
+  double g = FD_MUL(a, y);
+  const double h = FD_MUL(0.5, y);
+  g = FD_FMA(FD_FMA(-g, g, a), h, g);           // final correction
+  return g;
+}
+
+// sin(pi t), cos(pi t) for 0 < t < 2 (fdlibm k_sin.c / k_cos.c polynomials on |pi*y| <= pi/4).
+__device__ __forceinline__ void sincospi_02(double t, double& sn, double& cs) {
+  const double qd = rint(FD_ADD(t, t));         // nearest quarter-turn index 0..4
+  const int q = (int)qd;
+  const double y = FD_FMA(qd, -0.5, t);         // exact, |y| <= 1/4
+  const double r = FD_FMA(y, 1.2246467991473532e-16, FD_MUL(y, 3.141592653589793116));  // pi*y, pi = hi + lo
+  const double z = FD_MUL(r, r);
+  double ps = 1.58969099521155010221e-10;
+  ps = FD_FMA(ps, z, -2.50507602534068634195e-08);
+  ps = FD_FMA(ps, z, 2.75573137070700676789e-06);
+  ps = FD_FMA(ps, z, -1.98412698298579493134e-04);
+  ps = FD_FMA(ps, z, 8.33333333332248946124e-03);
+  ps = FD_FMA(ps, z, -1.66666666666666324348e-01);
+  const double s = FD_FMA(FD_MUL(r, z), ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = FD_FMA(pc, z, 2.08757232129817482790e-09);
+  pc = FD_FMA(pc, z, -2.75573143513906633035e-07);
+  pc = FD_FMA(pc, z, 2.48015872894767294178e-05);
+  pc = FD_FMA(pc, z, -1.38888888888741095749e-03);
+  pc = FD_FMA(pc, z, 4.16666666666666019037e-02);
+  const double c = FD_FMA(z, FD_FMA(z, pc, -0.5), 1.0);
+  // t = q/2 + y:  q odd -> (sin, cos) = (+-cos, -+sin) of pi*y
+  const bool swap = q & 1;
+  double a = swap ? c : s;
+  double b = swap ? s : c;
+  if (q & 2) a = -a;
+  if ((q + 1) & 2) b = -b;
+  sn = a;
+  cs = b;
+}
+
 __device__ __forceinline__ Normal2 normal_pair(uint64_t seed, uint64_t id, uint64_t t, uint32_t stream) {
   uint32_t w[4];
   philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (stream << 24) | ((uint32_t)(t >> 32) & 0xFFFFFFu),
                 (uint32_t)seed, (uint32_t)(seed >> 32), w);
   const double u1 = u52_to_open_unit(w[0], w[1]);
   const double u2 = u52_to_open_unit(w[2], w[3]);
-  const double R = __dsqrt_rn(__dmul_rn(-2.0, log(u1)));
+  const double R = sqrt_pos(FD_MUL(-2.0, log_unit(u1)));
   double sn, cs;
-  sincospi(__dmul_rn(2.0, u2), &sn, &cs);
+  sincospi_02(FD_ADD(u2, u2), sn, cs);
   Normal2 out;
-  out.z0 = __dmul_rn(R, cs);
-  out.z1 = __dmul_rn(R, sn);
+  out.z0 = FD_MUL(R, cs);
+  out.z1 = FD_MUL(R, sn);
   return out;
 }
 

@@ -7,12 +7,23 @@
 // K4: fixed-shape reduction of per-env returns to per-group statistics.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dynamics.cuh"
 #include "kernel_args.cuh"
 #include "philox.cuh"
 
 namespace fishing {
+
+// FISHING_GENERIC_ROLLOUT=1 forces the generic K2 kernel (A/B checks of the fast path)
+static bool generic_only() {
+  static const bool on = [] {
+    const char* e = std::getenv("FISHING_GENERIC_ROLLOUT");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
 
 // The two environments a thread owns.  Default layout: adjacent ids (2j, 2j+1) -> 16-byte vector accesses.
 // Sweep layout (noise_id_div = m > 1, env id = replicate*m + level): thread = (replicate pair, level), i.e. ids
@@ -263,16 +274,184 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
   if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
 }
 
+// ------------------------------------------------------------------------------------------------ K2, fast path
+// The configuration the big rollouts use (Box action space, no traces, in-kernel noise or none) with everything that
+// is loop-invariant resolved at compile time and a handful of comparisons removed that can never fire:
+//   * max(x - h, 0.0) (base_fishing_env.py:118) is the identity because h = min(x, quota) <= x (or NaN) always;
+//   * "stock <= 0" is the negation of the comparison np.maximum already makes;
+//   * the lower clip of the action is dead for the escapement / MSY policies: a = q/K - 1 with q = max(., 0) >= 0.
+// Results are bit-identical to the generic kernel (tests/test_gpu_parity.py runs both against the oracle).
+struct FastEnv {
+  double s, K, r, S, ret, quota_const;
+  int years, done_step;
+  bool frozen;
+};
+
+template <int GROWTH, int PM, int POLICY, bool NOISY>
+__device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
+                                              uint64_t gid, bool auto_reset, bool freeze) {
+  double x = __dadd_rn(e.s, 1.0);
+  if (PM != P_KONE) x = __dmul_rn(x, e.K);
+  double quota;
+  if (POLICY == FISHING_POLICY_ESCAPEMENT) {
+    const double q = py_max(__dsub_rn(x, e.S), 0.0);            // policies.py:29
+    double act = action_cts<PM>(q, e.K);                         // get_action, base_fishing_env.py:156
+    act = (act > 1.0) ? 1.0 : act;                               // np.clip: the lower bound cannot fire (act >= -1)
+    quota = __dadd_rn(act, 1.0);
+    if (PM != P_KONE) quota = __dmul_rn(quota, e.K);
+  } else if (POLICY == FISHING_POLICY_MSY) {
+    quota = e.quota_const;
+  } else {
+    quota = quota_f64<PM>(action, e.K);
+  }
+  const double h = py_min(x, quota);
+  const double x1 = __dsub_rn(x, h);                             // == max(x - h, 0.0)
+  const double frac = PM == P_KONE ? x1 : __ddiv_rn(x1, e.K);
+  const double room = __dsub_rn(1.0, frac);
+  double g;
+  if (GROWTH == LOGISTIC) {
+    g = __dadd_rn(x1, __dmul_rn(__dmul_rn(e.r, x1), room));
+    if (NOISY) g = __dadd_rn(g, __dmul_rn(__dmul_rn(x1, a.sigma), z));
+  } else {
+    double ex = __dmul_rn(__dmul_rn(e.r, room), __dsub_rn(x1, a.C));
+    if (NOISY) ex = __dadd_rn(ex, __dmul_rn(__dmul_rn(x1, a.sigma), z));
+    g = __dmul_rn(x1, exp(ex));
+  }
+  const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
+  const double x2 = alive ? g : 0.0;
+  const double s2 = __dsub_rn(PM == P_KONE ? x2 : __ddiv_rn(x2, e.K), 1.0);
+  const double reward = py_max(h, 0.0);
+  e.years += 1;
+  const bool done = (e.years > a.Tmax) || !alive;
+  if (auto_reset || e.done_step < 0) e.ret = __dadd_rn(e.ret, reward);
+  e.s = s2;
+  if (done) {
+    if (e.done_step < 0) e.done_step = t;
+    if (auto_reset) {
+      e.years = 0;
+      if (PM == P_PERENV) {
+        const Normal2 d = normal_pair(a.seed, gid, a.step0 + (uint64_t)t, FISHING_STREAM_AUTORESET);
+        e.K = v4_param(a.K_mean, a.sigma_p, d.z0);
+        e.r = v4_param(a.r_mean, a.sigma_p, d.z1);
+        if (POLICY == FISHING_POLICY_MSY) {
+          double unused;
+          e.quota_const = policy_quota_msy<PM>(a, e.K, unused);
+        }
+      }
+      e.s = a.s_reset;
+    } else if (freeze) {
+      e.frozen = true;
+    }
+  }
+}
+
+template <int GROWTH, int PM, int POLICY, bool NOISY>
+__global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (a.n >> 1)) return;
+  Lanes L;
+  uint64_t noise_pair;
+  const int64_t m = a.noise_id_div;
+  if (m > 1) {
+    const int64_t kp = tid / m, j = tid - kp * m;
+    L.i0 = (2 * kp) * m + j;
+    L.i1 = L.i0 + m;
+    L.vec = false;
+    noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
+  } else {
+    L.i0 = 2 * tid;
+    L.i1 = L.i0 + 1;
+    L.vec = true;
+    noise_pair = ((uint64_t)a.env_id0 >> 1) + (uint64_t)tid;
+  }
+  const uint64_t gid0 = (uint64_t)(a.env_id0 + L.i0), gid1 = (uint64_t)(a.env_id0 + L.i1);
+  const bool auto_reset = a.flags & FISHING_AUTO_RESET;
+  const bool freeze = !auto_reset && (a.flags & FISHING_FREEZE_DONE);
+
+  FastEnv e0, e1;
+  {
+    const double2 s = load2<double2>(a.state, L);
+    const int2 y = load2<int2>(a.years, L);
+    e0.s = s.x; e1.s = s.y;
+    e0.years = y.x; e1.years = y.y;
+    e0.K = e1.K = a.K;
+    e0.r = e1.r = a.r;
+    if (PM == P_PERENV) {
+      const double2 K = load2<double2>(a.K_env, L), r = load2<double2>(a.r_env, L);
+      e0.K = K.x; e1.K = K.y; e0.r = r.x; e1.r = r.y;
+    }
+    e0.S = e1.S = a.S;
+    if (POLICY == FISHING_POLICY_ESCAPEMENT && a.S_env) {
+      const double2 S = load2<double2>(a.S_env, L);
+      e0.S = S.x; e1.S = S.y;
+    }
+    e0.ret = e1.ret = 0.0;
+    e0.done_step = e1.done_step = -1;
+    e0.frozen = e1.frozen = false;
+    e0.quota_const = e1.quota_const = 0.0;
+    if (POLICY == FISHING_POLICY_MSY) {
+      double unused;
+      e0.quota_const = policy_quota_msy<PM>(a, e0.K, unused);
+      e1.quota_const = policy_quota_msy<PM>(a, e1.K, unused);
+    }
+  }
+  const int T = (int)a.T;
+  const double* act_base = reinterpret_cast<const double*>(a.actions);
+  double2 act_next = make_double2(0.0, 0.0);
+  if (POLICY == FISHING_POLICY_ACTIONS && T > 0) act_next = load2_stream<double2>(act_base, L);
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    double2 act = act_next;
+    if (POLICY == FISHING_POLICY_ACTIONS && t + 1 < T) act_next = load2_stream<double2>(act_base + (int64_t)(t + 1) * a.n, L);
+    double z0 = 0.0, z1 = 0.0;
+    if (NOISY) {
+      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      z0 = d.z0; z1 = d.z1;
+    }
+    if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY>(a, e0, act.x, z0, t, gid0, auto_reset, freeze);
+    if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY>(a, e1, act.y, z1, t, gid1, auto_reset, freeze);
+    if (freeze && e0.frozen && e1.frozen) break;
+  }
+
+  store2<double2>(a.state, L, e0.s, e1.s);
+  store2<int2>(a.years, L, e0.years, e1.years);
+  if (PM == P_PERENV) {
+    store2<double2>(a.K_env, L, e0.K, e1.K);
+    store2<double2>(a.r_env, L, e0.r, e1.r);
+  }
+  if (a.out_return) store2<double2>(a.out_return, L, e0.ret, e1.ret);
+  if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
+}
+
+template <int GROWTH, int PM, int POLICY>
+static void launch_fast_n(const RolloutArgs& a, bool noisy, int grid, int block, cudaStream_t st) {
+  if (noisy) rollout_fast_kernel<GROWTH, PM, POLICY, true><<<grid, block, 0, st>>>(a);
+  else rollout_fast_kernel<GROWTH, PM, POLICY, false><<<grid, block, 0, st>>>(a);
+}
+
 template <int GROWTH, int PM>
 static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream_t st) {
   const int64_t threads = a.n >> 1;
   const int block = 128;
   const int64_t grid = (threads + block - 1) / block;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  switch (policy) {
-    case FISHING_POLICY_ACTIONS: rollout_kernel<GROWTH, PM, FISHING_POLICY_ACTIONS><<<(int)grid, block, 0, st>>>(a); break;
-    case FISHING_POLICY_ESCAPEMENT: rollout_kernel<GROWTH, PM, FISHING_POLICY_ESCAPEMENT><<<(int)grid, block, 0, st>>>(a); break;
-    default: rollout_kernel<GROWTH, PM, FISHING_POLICY_MSY><<<(int)grid, block, 0, st>>>(a); break;
+  const bool tracing = a.trace_obs || a.trace_reward || a.trace_done || a.trace_action;
+  const bool fast = !a.discrete && !tracing && !a.noise && a.T <= 0x7fffffffLL &&
+                    (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
+  if (fast) {
+    const bool noisy = a.sigma != 0.0;
+    switch (policy) {
+      case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, (int)grid, block, st); break;
+      case FISHING_POLICY_ESCAPEMENT: launch_fast_n<GROWTH, PM, FISHING_POLICY_ESCAPEMENT>(a, noisy, (int)grid, block, st); break;
+      default: launch_fast_n<GROWTH, PM, FISHING_POLICY_MSY>(a, noisy, (int)grid, block, st); break;
+    }
+  } else {
+    switch (policy) {
+      case FISHING_POLICY_ACTIONS: rollout_kernel<GROWTH, PM, FISHING_POLICY_ACTIONS><<<(int)grid, block, 0, st>>>(a); break;
+      case FISHING_POLICY_ESCAPEMENT: rollout_kernel<GROWTH, PM, FISHING_POLICY_ESCAPEMENT><<<(int)grid, block, 0, st>>>(a); break;
+      default: rollout_kernel<GROWTH, PM, FISHING_POLICY_MSY><<<(int)grid, block, 0, st>>>(a); break;
+    }
   }
   count_launch();
   return cudaGetLastError();

@@ -57,71 +57,68 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
 }
 
 // ------------------------------------------------------------------------------------------------ K1, vector path
-// Each thread owns PAIRS of adjacent environments (2j, 2j+1): 16-byte loads/stores for the float64 arrays, one
-// Philox block + one Box-Muller per pair.  UNROLL independent pairs per thread keep several loads in flight.
-template <int GROWTH, int PM, int ACT, int UNROLL>
-__global__ void __launch_bounds__(256) step_kernel_vec2(const StepArgs a) {
+// One thread owns ONE PAIR of adjacent environments (2j, 2j+1): 16-byte loads/stores on the float64 arrays, one Philox
+// block + one Box-Muller for the pair.  128-thread blocks, one pair per thread -> 4096 blocks at n = 2^20: fine-grained
+// enough that the tail of launch t is filled by the head of launch t+1 when programmatic dependent launch is on.
+//
+// The kernel has two phases.  Phase A touches only this launch's own inputs (actions, injected noise) and does all the
+// state-independent work -- the Philox rounds and the fp64 Box-Muller, i.e. most of the instructions.  Phase B reads
+// the state written by the previous launch.  With PDL (sm_90+ `griddepcontrol`) every block first releases the next
+// launch in the stream, and waits for the previous launch only between the phases, so consecutive lock-steps overlap:
+// the next step's noise is generated while this step drains.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <int GROWTH, int PM, int ACT>
+__global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
-  const int64_t npairs = a.n >> 1;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
+  const int npairs = (int)(a.n >> 1);
+  const int j = (int)(blockIdx.x * 128u + threadIdx.x);
+  const bool live = j < npairs;
   const bool ext_noise = a.noise != nullptr;
   const bool noisy = ext_noise || a.sigma != 0.0;
-  const uint64_t pair0 = (uint64_t)a.env_id0 >> 1;
 
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < npairs; base += stride * UNROLL) {
-    double2 s[UNROLL], z[UNROLL], Kv[UNROLL], rv[UNROLL];
-    AT2 act[UNROLL];
-    int2 yr[UNROLL];
-    bool live[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t j = base + u * stride;
-      live[u] = j < npairs;
-      if (live[u]) {
-        act[u] = ld_stream(reinterpret_cast<const AT2*>(a.action) + j);
-        if (ext_noise) z[u] = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
-        s[u] = reinterpret_cast<const double2*>(a.state_in)[j];
-        yr[u] = reinterpret_cast<const int2*>(a.years)[j];
-        if (PM == P_PERENV) {
-          Kv[u] = reinterpret_cast<const double2*>(a.K_env)[j];
-          rv[u] = reinterpret_cast<const double2*>(a.r_env)[j];
-        }
-      }
+  // ---- phase A: independent of the previous launch
+  AT2 act = {};
+  double2 z = make_double2(0.0, 0.0);
+  if (live) {
+    act = ld_stream(reinterpret_cast<const AT2*>(a.action) + j);
+    if (ext_noise) {
+      z = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
+    } else if (noisy) {
+      const Normal2 d = normal_pair(a.seed, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
+      z = make_double2(d.z0, d.z1);
     }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if (!live[u]) continue;
-      const int64_t j = base + u * stride;
-      if (PM != P_PERENV) {
-        Kv[u] = make_double2(a.K, a.K);
-        rv[u] = make_double2(a.r, a.r);
-      }
-      if (!ext_noise) {
-        if (noisy) {
-          const Normal2 d = normal_pair(a.seed, pair0 + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
-          z[u] = make_double2(d.z0, d.z1);
-        } else {
-          z[u] = make_double2(0.0, 0.0);
-        }
-      }
-      const EnvResult e0 = advance<GROWTH, PM, ACT>(a, 2 * j, s[u].x, act[u].x, z[u].x, noisy, yr[u].x, Kv[u].x, rv[u].x);
-      const EnvResult e1 = advance<GROWTH, PM, ACT>(a, 2 * j + 1, s[u].y, act[u].y, z[u].y, noisy, yr[u].y, Kv[u].y, rv[u].y);
-      reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
-      st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
-      st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
-      reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
-      if (a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
-      if (a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
-      if (e0.reset_fired | e1.reset_fired) {
-        if (a.out_terminal) {
-          if (e0.reset_fired) a.out_terminal[2 * j] = e0.terminal;
-          if (e1.reset_fired) a.out_terminal[2 * j + 1] = e1.terminal;
-        }
-        if (PM == P_PERENV) {
-          reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
-          reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
-        }
-      }
+  }
+  if (a.flags & STEP_FLAG_PDL) pdl_wait();
+  if (!live) return;
+
+  // ---- phase B: state written by the previous launch
+  const double2 s = reinterpret_cast<const double2*>(a.state_in)[j];
+  const int2 yr = reinterpret_cast<const int2*>(a.years)[j];
+  double2 Kv = make_double2(a.K, a.K), rv = make_double2(a.r, a.r);
+  if (PM == P_PERENV) {
+    Kv = reinterpret_cast<const double2*>(a.K_env)[j];
+    rv = reinterpret_cast<const double2*>(a.r_env)[j];
+  }
+  const int64_t i0 = 2 * (int64_t)j;
+  const EnvResult e0 = advance<GROWTH, PM, ACT>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x);
+  const EnvResult e1 = advance<GROWTH, PM, ACT>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y);
+  reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
+  st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
+  st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
+  reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
+  if (a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
+  if (a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
+  if (e0.reset_fired | e1.reset_fired) {
+    if (a.out_terminal) {
+      if (e0.reset_fired) a.out_terminal[i0] = e0.terminal;
+      if (e1.reset_fired) a.out_terminal[i0 + 1] = e1.terminal;
+    }
+    if (PM == P_PERENV) {
+      reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
+      reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
     }
   }
 }
@@ -344,11 +341,26 @@ static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
 
 template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
-  constexpr int UNROLL = 2;
   if (vec) {
     const int64_t npairs = a.n >> 1;
-    const int grid = grid_for((npairs + UNROLL - 1) / UNROLL, 256, 8);
-    step_kernel_vec2<GROWTH, PM, ACT, UNROLL><<<grid, 256, 0, st>>>(a);
+    const int64_t blocks = (npairs + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (a.flags & STEP_FLAG_PDL) {
+      // programmatic dependent launch: this grid may start while the previous kernel in the stream is still draining
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)blocks);
+      cfg.blockDim = dim3(128);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      count_launch();
+      return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT>, a);
+    }
+    step_kernel_vec2<GROWTH, PM, ACT><<<(unsigned)blocks, 128, 0, st>>>(a);
   } else {
     const int grid = grid_for(a.n, 256, 8);
     step_kernel_scalar<GROWTH, PM, ACT><<<grid, 256, 0, st>>>(a);

@@ -50,7 +50,12 @@ enum fishing_action_dtype {
 
 enum fishing_flags {
   FISHING_AUTO_RESET = 1u << 0, /* stable-baselines3 VecEnv semantics: reset an env in the step that ends it */
-  FISHING_FREEZE_DONE = 1u << 1 /* rollout only: stop stepping an env after its first done                 */
+  FISHING_FREEZE_DONE = 1u << 1, /* rollout only: stop stepping an env after its first done                 */
+  FISHING_PDL = 1u << 2          /* step only: launch with programmatic dependent launch.  The caller guarantees
+                                    that the action / noise buffers of this step are not written by the kernel
+                                    that immediately precedes it on the stream (the state, years and output
+                                    buffers may be: the kernel waits for its predecessor before touching them).
+                                    fishing_step_many sets this by itself.                                      */
 };
 
 enum fishing_policy {

@@ -236,6 +236,26 @@ def test_philox_noise_matches_numpy_restatement_and_is_partition_invariant():
     assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
 
 
+def test_philox_normals_against_long_double_evaluation():
+    """The hand-written log / sqrt / sincospi of csrc/philox.cuh against an 80-bit evaluation of the same formulas."""
+    n = 1 << 16
+    b = make_batch("v1", n, seed=7, sigma=0.1)
+    z = b.noise(4, step0=123).cpu().numpy()
+    ld = np.longdouble
+    pi = ld("3.14159265358979323846264338327950288")
+    for t in range(4):
+        pairs = np.arange(n // 2, dtype=np.uint64)
+        u1, u2 = pr.uniforms(7, pairs, np.uint64(123 + t), 0)
+        R = np.sqrt(ld(-2) * np.log(u1.astype(ld)))
+        z0 = (R * np.cos(ld(2) * pi * u2.astype(ld))).astype(np.float64)
+        z1 = (R * np.sin(ld(2) * pi * u2.astype(ld))).astype(np.float64)
+        ref = np.empty(n)
+        ref[0::2], ref[1::2] = z0, z1
+        err = np.abs(z[t] - ref)
+        assert err.max() < 3e-15, err.max()
+        assert np.mean(err == 0) > 0.5   # most draws are correctly rounded
+
+
 @pytest.mark.parametrize("kind", ["v1", "v2", "v4"])
 def test_in_kernel_noise_equals_exported_noise(kind):
     """The stochastic-parity protocol: export the engine's own draws, inject them into the oracle."""
@@ -303,6 +323,20 @@ def test_fused_rollout_matches_oracle_and_single_steps(kind, cfg, policy):
     same(out["ret"].cpu().numpy(), exp["ret"], kind, "return", cfg["K"] * T)
     assert np.array_equal(out["done_step"].cpu().numpy(), exp["done_step"])
     same(b.state.cpu().numpy(), exp["final_state"], kind, "final state", cfg["K"])
+    # the specialised no-trace kernel must agree with the traced (generic) one bit for bit
+    b2 = make_batch(kind, n, **cfg)
+    b2.reset(reset_noise=dev(rn0) if kind == "v4" else None)
+    sig = cfg["sigma"]
+    for batch in (b, b2):
+        batch.cfg["sigma"] = 0.0   # the fast path has no injected-noise input: compare both kernels at sigma = 0
+    b.reset(reset_noise=dev(rn0) if kind == "v4" else None)
+    kw = dict(policy=policy, S=S, msy_q=msy_q,
+              actions=dev(acts, torch.int64 if kind == "v0" else torch.float64) if policy == "actions" else None)
+    slow = b.rollout(T, trace=True, **kw)
+    fast = b2.rollout(T, **kw)
+    assert torch.equal(slow["ret"], fast["ret"]) and torch.equal(slow["done_step"], fast["done_step"])
+    assert torch.equal(b.state, b2.state) and torch.equal(b.years, b2.years)
+    b.cfg["sigma"] = sig
 
 
 def test_fused_rollout_with_philox_equals_T_single_steps_bitwise():
@@ -557,3 +591,28 @@ def test_edge_cases_through_scalar_api():
                 same(obs[0], fo.unhex(es), kind, str(case))
                 same(r, fo.unhex(er), kind, str(case))
                 assert d is ed
+
+
+@pytest.mark.parametrize("kind,cfg", [c for c in CASES if c[0] != "v0"])
+@pytest.mark.parametrize("mode", ["plain", "auto_reset", "freeze"])
+def test_fast_rollout_kernel_equals_generic_kernel_with_philox(kind, cfg, mode, monkeypatch):
+    """K2's specialised kernel (in-kernel Philox, no traces) against the generic one, which is checked against the
+    oracle above.  FISHING_GENERIC_ROLLOUT is read once per process, so the generic result comes from the traced call."""
+    torch = _torch()
+    n, T = 4096, 120
+    rng = np.random.default_rng(11)
+    acts = dev(rng.uniform(-1.0, -0.7, size=(T, n)))
+    S = float(np.float32(0.45 * cfg["K"]))
+    for policy in ("escapement", "msy", "actions"):
+        res = []
+        for traced in (True, False):
+            b = make_batch(kind, n, auto_reset=(mode == "auto_reset"), seed=3, **cfg)
+            b.reset()
+            out = b.rollout(T, policy=policy, S=S, msy_q=float(np.float32(0.05 * cfg["K"])),
+                            actions=acts if policy == "actions" else None, freeze_done=(mode == "freeze"), trace=traced)
+            res.append((out["ret"].clone(), out["done_step"].clone(), b.state.clone(), b.years.clone(),
+                        None if b.K_env is None else b.K_env.clone()))
+        for x, y in zip(*res):
+            if x is not None:
+                assert torch.equal(x, y), (kind, mode, policy)
+        assert (res[0][1] >= 0).any()
