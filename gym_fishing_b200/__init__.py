@@ -14,5 +14,6 @@ from .envs import BaseFishingEnv, FishingCtsEnv, FishingEnv, FishingModelError, 
 from .vec_env import FishingVecEnv  # noqa: F401
 from .engine import EnvBatch, bmsy  # noqa: F401
 from .models.policies import BMSY, escapement, msy  # noqa: F401
+from .rollouts import escapement_sweep, rollout_stats  # noqa: F401
 
 __version__ = "0.1.0"

@@ -338,8 +338,13 @@ int fishing_vec_create(const fishing_params* p, int64_t n, int64_t env_id0, int3
   }
   v->d_obs = v->soa.state;
   cudaMemset(v->d_terminal, 0xFF, nd);  // NaN until an episode actually ends
-  // ~6 chunks in flight hide the first H2D / last D2H; chunks stay even and 16-byte aligned
-  int64_t chunk = (n + 5) / 6;
+  // a few chunks in flight hide the first H2D / last D2H; chunks stay even and 16-byte aligned
+  int64_t nchunks = 2;
+  if (const char* e = std::getenv("FISHING_VEC_CHUNKS")) {
+    const long v = std::atol(e);
+    if (v >= 1 && v <= 64) nchunks = v;
+  }
+  int64_t chunk = (n + nchunks - 1) / nchunks;
   chunk = (chunk + 1023) / 1024 * 1024;
   if (chunk > n) chunk = n;
   v->chunk = chunk;

@@ -57,6 +57,7 @@ class EnvBatch:
         torch = nat.require_cuda()
         nat.lib()
         self.torch = torch
+        self._lib = nat.lib()
         self.kind = int(kind)
         self.n = int(n)
         self.device = torch.device(device)
@@ -133,12 +134,14 @@ class EnvBatch:
         if out_terminal is not None:
             _chk_dev(out_terminal, "out_terminal", torch.float64, self.n)
         p = self.params()
-        with torch.cuda.device(self.device):
-            rc = nat.lib().fishing_step(ct.byref(p), self.n, self.env_id0, self.step_idx, action.data_ptr(), adt,
-                                        _ptr(noise), _ptr(reset_noise), self.soa(src), out_obs.data_ptr(),
-                                        out_reward.data_ptr(), out_done.data_ptr(), _ptr(out_terminal),
-                                        _ptr(out_stock), _ptr(out_harvest), _stream(self.device))
-        nat.check(rc, "fishing_step")
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
+        rc = self._lib.fishing_step(ct.byref(p), self.n, self.env_id0, self.step_idx, action.data_ptr(), adt,
+                                    _ptr(noise), _ptr(reset_noise), self.soa(src), out_obs.data_ptr(),
+                                    out_reward.data_ptr(), out_done.data_ptr(), _ptr(out_terminal),
+                                    _ptr(out_stock), _ptr(out_harvest), torch.cuda.current_stream().cuda_stream)
+        if rc:
+            nat.check(rc, "fishing_step")
         self.step_idx += 1
         self.state = out_obs  # the newest observations ARE the state (no copy)
         return out_obs, out_reward, out_done
