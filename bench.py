@@ -307,13 +307,30 @@ def run_gpu(args):
     barrier()
     t0 = time.perf_counter()
     acc = 0.0
-    for t in range(e2e_T):
+    per_step_T = min(e2e_T, 50)
+    for t in range(per_step_T):
         o, r_, d_, _ = venv.step(h_act[t % 8])
         acc += float(r_[0])
     torch.cuda.synchronize()
+    per_step_ms = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev)
+    e2e_per_step = world * n * per_step_T / (per_step_ms * 1e-3)
+    # whole-rollout host call: actions [T, n] in pinned host memory -> obs / reward / done [T, n] in pinned host memory
+    chunk_T = 8
+    p_obs, p_rew, p_done = _PinnedArray(chunk_T * n, np.float64), _PinnedArray(chunk_T * n, np.float64), _PinnedArray(chunk_T * n, np.uint8)
+    outs = (p_obs.array.reshape(chunk_T, n), p_rew.array.reshape(chunk_T, n), p_done.array.reshape(chunk_T, n))
+    venv.step_many(h_act, out=outs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_T // chunk_T):
+        o, r_, d_ = venv.step_many(h_act, out=outs)
+        acc += float(r_[-1, 0])
+    torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = barrier_max_ms(e2e_ms, dev)
+    e2e_T = (e2e_T // chunk_T) * chunk_T
     e2e_value = world * n * e2e_T / (e2e_ms * 1e-3)
+    for pa in (p_obs, p_rew, p_done):
+        pa.free()
     venv.close()
     pinned.free()
 
@@ -341,7 +358,9 @@ def run_gpu(args):
                          "avg_launch_us": k1_us, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * e2e_T, "d2h_bytes_per_step": n * 17 * e2e_T,
-                    "lock_steps_timed": e2e_T, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step (pinned host buffers)"},
+                    "lock_steps_timed": e2e_T,
+                    "api": "FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, 8 lock-steps per call)",
+                    "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"}},
             "fused": fused,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),

@@ -24,7 +24,7 @@ EXPORTS = (
     "fishing_abi_version", "fishing_error_string", "fishing_launch_count", "fishing_reset", "fishing_step",
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
-    "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal",
+    "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
 )
 
 
@@ -80,6 +80,8 @@ def lib():
     L.fishing_step.argtypes = [P, i64, i64, u64, vp, i32, vp, vp, FishingSoA, vp, vp, vp, vp, vp, vp, vp]
     L.fishing_step_many.restype = C.c_int
     L.fishing_step_many.argtypes = [P, i64, i64, u64, i64, vp, i32, vp, FishingSoA, vp, vp, vp, vp, vp]
+    L.fishing_vec_step_many.restype = C.c_int
+    L.fishing_vec_step_many.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     L.fishing_vec_fetch_terminal.restype = C.c_int
     L.fishing_vec_fetch_terminal.argtypes = [vp, vp]
     L.fishing_noise_fill.restype = C.c_int

@@ -423,6 +423,51 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
   return rc;
 }
 
+int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, double* obs_out,
+                          double* reward_out, uint8_t* done_out) {
+  if (!v || !actions || !obs_out || !reward_out || !done_out || T < 0) return FISHING_E_ARG;
+  if (!v->was_reset) return FISHING_E_STATE;
+  const int asz = act_size(action_dtype);
+  if (!asz) return FISHING_E_ARG;
+  if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  // a fixed chunk -> stream assignment keeps every dependency (state, staging buffers) inside one in-order stream;
+  // the three streams keep an H2D, a kernel and a D2H of different chunks in flight at the same time
+  const int64_t n = v->n;
+  int64_t chunk = ((n + 2) / 3 + 1023) / 1024 * 1024;
+  if (chunk > n) chunk = n;
+  int rc = 0;
+  for (int64_t t = 0; t < T && rc == 0; ++t) {
+    int k = 0;
+    for (int64_t off = 0; off < n && rc == 0; off += chunk, ++k) {
+      const int64_t len = (n - off < chunk) ? n - off : chunk;
+      cudaStream_t st = v->streams[k % 3];
+      char* d_act = static_cast<char*>(v->d_action) + off * asz;
+      e = cudaMemcpyAsync(d_act, static_cast<const char*>(actions) + (t * n + off) * asz, (size_t)len * asz,
+                          cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { rc = (int)e; break; }
+      fishing_soa s = v->soa;
+      s.state += off; s.years += off;
+      if (s.K_env) { s.K_env += off; s.r_env += off; }
+      rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, nullptr, nullptr, s, v->d_obs + off,
+                        v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, st);
+      if (rc) break;
+      e = cudaMemcpyAsync(obs_out + t * n + off, v->d_obs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(reward_out + t * n + off, v->d_reward + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(done_out + t * n + off, v->d_done + off, (size_t)len, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) rc = (int)e;
+    }
+    v->step_idx += 1;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e = cudaStreamSynchronize(v->streams[i]);
+    if (e != cudaSuccess && rc == 0) rc = (int)e;
+  }
+  return rc;
+}
+
 int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out) {
   if (!v || !terminal_out) return FISHING_E_ARG;
   cudaError_t e = cudaSetDevice(v->device);

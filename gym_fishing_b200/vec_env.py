@@ -258,6 +258,42 @@ class FishingVecEnv:
         return (self._h_obs.array.reshape(n, 1), self._h_reward.array, done,
                 LazyInfos(done, _LazyTerminal(self) if self.auto_reset else None))
 
+    def step_many(self, actions, out=None):
+        """T = actions.shape[0] lock-steps in one call (the loop of simulate_mdp_vec with a pre-computed action table).
+        numpy mode: actions [T, n] host array -> (obs [T, n], rewards [T, n], dones [T, n]) host arrays, with the copies
+        and kernels of consecutive steps pipelined (fishing_vec_step_many).  `out` may supply the three output arrays
+        (e.g. page-locked ones).  torch mode: CUDA tensors in and out (fishing_step_many)."""
+        self._check_open()
+        n = self.num_envs
+        if self.io == "torch":
+            torch = self.batch.torch
+            a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions), device=self.device)
+            T = a.shape[0]
+            a = a.reshape(T, n).contiguous()
+            if out is None:
+                out = (torch.empty((T, n), dtype=torch.float64, device=self.device),
+                       torch.empty((T, n), dtype=torch.float64, device=self.device),
+                       torch.empty((T, n), dtype=torch.uint8, device=self.device))
+            self.batch.step_many(a, out[0], out[1], out[2])
+            return out[0], out[1], out[2].view(torch.bool)
+        a = np.asarray(actions)
+        T = a.shape[0]
+        if self.kind == nat.V0:
+            adt = nat.ACT_I32 if a.dtype == np.int32 else nat.ACT_I64
+            a = a if a.dtype == np.int32 else a.astype(np.int64, copy=False)
+        else:
+            adt = nat.ACT_F32 if a.dtype == np.float32 else nat.ACT_F64
+            a = a if a.dtype == np.float32 else a.astype(np.float64, copy=False)
+        a = np.ascontiguousarray(a.reshape(T, n))
+        if out is None:
+            out = (np.empty((T, n)), np.empty((T, n)), np.empty((T, n), dtype=np.uint8))
+        obs, rew, done = out
+        rc = nat.lib().fishing_vec_step_many(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data,
+                                             done.ctypes.data)
+        nat.check(rc, "fishing_vec_step_many")
+        self._steps_done += T
+        return obs, rew, done.view(np.bool_)
+
     # ------------------------------------------------------------------------------------------------ attributes
     def _indices(self, indices):
         if indices is None:

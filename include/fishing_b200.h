@@ -237,6 +237,10 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
 /* page-locked host memory helpers so that callers can make their numpy buffers DMA-able */
 int fishing_host_alloc(void** ptr, int64_t bytes);
 int fishing_host_free(void* ptr);
+/* T lock-steps in one call: actions[T, n] in, obs / reward / done [T, n] out (all host).  Copies and kernels of
+ * consecutive steps are pipelined over the handle's streams (the host-side counterpart of fishing_step_many). */
+int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, double* obs_out,
+                          double* reward_out, uint8_t* done_out);
 /* terminal observations of the most recent step (valid where that step reported done), fetched on demand so that the
  * per-step device-to-host traffic stays at obs + reward + done */
 int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out);

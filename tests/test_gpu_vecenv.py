@@ -167,3 +167,26 @@ def test_full_size_properties_2pow20():
     assert np.array_equal(obs[:, idx].cpu().numpy(), exp["obs"]) and np.array_equal(rew[:, idx].cpu().numpy(), exp["reward"])
     assert np.array_equal(done[:, idx].cpu().numpy(), exp["done"])
     assert 0.2 < exp["done"].mean() < 0.8
+
+
+def test_step_many_host_pipeline_equals_per_step_calls():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 5000, 12
+    rng = np.random.default_rng(4)
+    acts = rng.uniform(-1, -0.4, size=(T, n))
+    a = gf.FishingVecEnv("fishing-v1", num_envs=n, io="numpy", seed=9, sigma=0.1, Tmax=5)
+    b = gf.FishingVecEnv("fishing-v1", num_envs=n, io="numpy", seed=9, sigma=0.1, Tmax=5)
+    c = gf.FishingVecEnv("fishing-v1", num_envs=n, io="torch", seed=9, sigma=0.1, Tmax=5)
+    a.reset(), b.reset(), c.reset()
+    obs, rew, done = a.step_many(acts)
+    obs_t, rew_t, done_t = c.step_many(torch.as_tensor(acts, device="cuda"))
+    for t in range(T):
+        o, r, d, _ = b.step(acts[t])
+        assert np.array_equal(o[:, 0], obs[t]) and np.array_equal(r, rew[t]) and np.array_equal(d, done[t])
+    assert np.array_equal(obs_t.cpu().numpy(), obs) and np.array_equal(done_t.cpu().numpy(), done)
+    assert done.sum() > n
+    for v in (a, b, c):
+        v.close()
