@@ -14,7 +14,14 @@ LIB_PATH = os.path.join(_HERE, "libfishing_b200.so")
 
 # enums (include/fishing_b200.h)
 V0, V1, V2, V4 = 0, 1, 2, 4
-KIND_OF_ID = {"fishing-v0": V0, "fishing-v1": V1, "fishing-v2": V2, "fishing-v4": V4}
+V5, V6, V7, V8, V9, V10, V11 = 5, 6, 7, 8, 9, 10, 11
+KIND_OF_ID = {"fishing-v0": V0, "fishing-v1": V1, "fishing-v2": V2, "fishing-v4": V4, "fishing-v5": V5, "fishing-v6": V6,
+              "fishing-v7": V7, "fishing-v8": V8, "fishing-v9": V9, "fishing-v10": V10, "fishing-v11": V11}
+LOGNORMAL_KINDS = (V5, V6, V7, V8, V9, V10, V11)
+FN_ALLEN, FN_BEVERTON_HOLT, FN_MYERS, FN_MAY, FN_RICKER = 0, 1, 2, 3, 4
+FN_OF_NAME = {"allen": FN_ALLEN, "beverton_holt": FN_BEVERTON_HOLT, "myers": FN_MYERS, "may": FN_MAY, "ricker": FN_RICKER}
+MAX_MODELS = 5
+ABI_VERSION = 2
 ACT_F64, ACT_F32, ACT_I32, ACT_I64 = 0, 1, 2, 3
 AUTO_RESET, FREEZE_DONE = 1, 2
 POLICY_ACTIONS, POLICY_ESCAPEMENT, POLICY_MSY = 0, 1, 2
@@ -25,17 +32,27 @@ EXPORTS = (
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
+    "fishing_reset_models", "fishing_population_draw_ln",
 )
+
+
+class GrowthParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("r", "K", "C", "M", "theta", "q", "b", "a", "sigma")]
 
 
 class FishingParams(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_actions", C.c_int32), ("Tmax", C.c_int32), ("flags", C.c_uint32),
                 ("r", C.c_double), ("K", C.c_double), ("sigma", C.c_double), ("C", C.c_double), ("x0", C.c_double),
-                ("sigma_p", C.c_double), ("seed", C.c_uint64)]
+                ("sigma_p", C.c_double), ("seed", C.c_uint64),
+                # ABI v2: log-normal growth family
+                ("growth_K", C.c_double), ("M", C.c_double), ("theta", C.c_double), ("q", C.c_double), ("b", C.c_double),
+                ("a", C.c_double), ("alpha", C.c_double), ("n_models", C.c_int32), ("model_fn", C.c_int32 * MAX_MODELS),
+                ("model_params", GrowthParams * MAX_MODELS)]
 
 
 class FishingSoA(C.Structure):
-    _fields_ = [("state", C.c_void_p), ("years", C.c_void_p), ("K_env", C.c_void_p), ("r_env", C.c_void_p)]
+    _fields_ = [("state", C.c_void_p), ("years", C.c_void_p), ("K_env", C.c_void_p), ("r_env", C.c_void_p),
+                ("model", C.c_void_p)]
 
 
 class FishingRolloutArgs(C.Structure):
@@ -76,6 +93,10 @@ def lib():
     L.fishing_launch_count.argtypes = []
     L.fishing_reset.restype = C.c_int
     L.fishing_reset.argtypes = [P, i64, i64, u64, vp, vp, FishingSoA, vp, vp]
+    L.fishing_reset_models.restype = C.c_int
+    L.fishing_reset_models.argtypes = [P, i64, i64, u64, vp, vp, FishingSoA, vp, vp]
+    L.fishing_population_draw_ln.restype = C.c_int
+    L.fishing_population_draw_ln.argtypes = [P, i32, i64, vp, vp, vp, vp]
     L.fishing_step.restype = C.c_int
     L.fishing_step.argtypes = [P, i64, i64, u64, vp, i32, vp, vp, FishingSoA, vp, vp, vp, vp, vp, vp, vp]
     L.fishing_step_many.restype = C.c_int
@@ -110,8 +131,8 @@ def lib():
     L.fishing_host_free.argtypes = [vp]
     L.fishing_vec_soa.restype = C.c_int
     L.fishing_vec_soa.argtypes = [vp, C.POINTER(FishingSoA)]
-    if L.fishing_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {L.fishing_abi_version()} != 1; rebuild")
+    if L.fishing_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.fishing_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = L
     return L
 
@@ -122,10 +143,23 @@ def check(code, where):
 
 
 def make_params(kind, *, r=0.3, K=1.0, sigma=0.0, C_=0.5, x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1, seed=0,
-                flags=0):
-    return FishingParams(kind=int(kind), n_actions=int(n_actions), Tmax=int(Tmax), flags=int(flags), r=float(r),
-                         K=float(K), sigma=float(sigma), C=float(C_), x0=float(x0), sigma_p=float(sigma_p),
-                         seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+                flags=0, growth_K=None, M=1.0, theta=1.0, q=1.0, b=1.0, a=0.0, alpha=0.0, models=None):
+    """models (fishing-v11): list of (growth function name, params dict) in the order of the env's `models` list."""
+    p = FishingParams(kind=int(kind), n_actions=int(n_actions), Tmax=int(Tmax), flags=int(flags), r=float(r),
+                      K=float(K), sigma=float(sigma), C=float(C_), x0=float(x0), sigma_p=float(sigma_p),
+                      seed=int(seed) & 0xFFFFFFFFFFFFFFFF, growth_K=float(K if growth_K is None else growth_K),
+                      M=float(M), theta=float(theta), q=float(q), b=float(b), a=float(a), alpha=float(alpha))
+    if models:
+        if len(models) > MAX_MODELS:
+            raise ValueError(f"at most {MAX_MODELS} models")
+        p.n_models = len(models)
+        for i, (name, mp) in enumerate(models):
+            p.model_fn[i] = FN_OF_NAME[name]
+            g = p.model_params[i]
+            g.r, g.K, g.sigma = float(mp.get("r", 0.0)), float(mp.get("K", 1.0)), float(mp.get("sigma", 0.0))
+            g.C, g.M, g.theta = float(mp.get("C", 0.0)), float(mp.get("M", 1.0)), float(mp.get("theta", 1.0))
+            g.q, g.b, g.a = float(mp.get("q", 1.0)), float(mp.get("b", 1.0)), float(mp.get("a", 0.0))
+    return p
 
 
 def require_cuda():

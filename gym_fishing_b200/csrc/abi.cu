@@ -32,7 +32,35 @@ int sm_count() {
 
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-static bool kind_ok(int kind) { return kind == FISHING_V0 || kind == FISHING_V1 || kind == FISHING_V2 || kind == FISHING_V4; }
+static bool kind_ok(int kind) {
+  return kind == FISHING_V0 || kind == FISHING_V1 || kind == FISHING_V2 || kind == FISHING_V4 ||
+         (kind >= FISHING_V5 && kind <= FISHING_V11);
+}
+static bool is_lognormal(int kind) { return kind >= FISHING_V5 && kind <= FISHING_V11; }
+
+static GrowthP growth_of(const fishing_params* p) {
+  GrowthP g;
+  g.r = p->r; g.K = p->growth_K; g.C = p->C; g.M = p->M; g.theta = p->theta; g.q = p->q; g.b = p->b; g.a = p->a;
+  g.sigma = p->sigma;
+  return g;
+}
+
+static int fill_table(const fishing_params* p, ModelTable* t, double* any_sigma) {
+  std::memset(t, 0, sizeof(*t));
+  *any_sigma = 0.0;
+  if (p->kind != FISHING_V11) return 0;
+  if (p->n_models < 1 || p->n_models > FISHING_MAX_MODELS) return FISHING_E_ARG;
+  t->n_models = p->n_models;
+  for (int i = 0; i < p->n_models; ++i) {
+    if (p->model_fn[i] < FISHING_FN_ALLEN || p->model_fn[i] > FISHING_FN_RICKER) return FISHING_E_ARG;
+    t->fn[i] = p->model_fn[i];
+    const fishing_growth_params& m = p->model_params[i];
+    t->p[i].r = m.r; t->p[i].K = m.K; t->p[i].C = m.C; t->p[i].M = m.M; t->p[i].theta = m.theta; t->p[i].q = m.q;
+    t->p[i].b = m.b; t->p[i].a = m.a; t->p[i].sigma = m.sigma;
+    if (m.sigma != 0.0) *any_sigma = 1.0;
+  }
+  return 0;
+}
 
 static int act_size(int dt) {
   switch (dt) {
@@ -77,6 +105,8 @@ static int check_soa(const fishing_params* p, const fishing_soa& s) {
   if (p->kind == FISHING_V4 && (!s.K_env || !s.r_env)) return FISHING_E_ARG;
   if (!aligned(s.state, 8) || !aligned(s.years, 4)) return FISHING_E_ALIGN;
   if (p->kind == FISHING_V4 && (!aligned(s.K_env, 8) || !aligned(s.r_env, 8))) return FISHING_E_ALIGN;
+  if (p->kind == FISHING_V11 && !s.model) return FISHING_E_ARG;
+  if (p->kind == FISHING_V11 && !aligned(s.model, 4)) return FISHING_E_ALIGN;
   return 0;
 }
 
@@ -104,8 +134,22 @@ const char* fishing_error_string(int code) {
   return "fishing: unknown error";
 }
 
+static int reset_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                      const double* reset_noise, const int32_t* reset_model, fishing_soa soa, double* out_obs, void* stream);
+
 int fishing_reset(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
                   const double* reset_noise, fishing_soa soa, double* out_obs, void* stream) {
+  return reset_impl(p, n, env_id0, epoch, mask, reset_noise, nullptr, soa, out_obs, stream);
+}
+
+int fishing_reset_models(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                         const int32_t* reset_model, fishing_soa soa, double* out_obs, void* stream) {
+  if (reset_model && !aligned(reset_model, 4)) return FISHING_E_ALIGN;
+  return reset_impl(p, n, env_id0, epoch, mask, nullptr, reset_model, soa, out_obs, stream);
+}
+
+static int reset_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                      const double* reset_noise, const int32_t* reset_model, fishing_soa soa, double* out_obs, void* stream) {
   if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind)) return FISHING_E_ARG;
   if (int e = check_soa(p, soa)) return e;
   if (out_obs && !aligned(out_obs, 8)) return FISHING_E_ALIGN;
@@ -115,6 +159,11 @@ int fishing_reset(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t 
   a.s_reset = reset_state_value(p);
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
   a.per_env = p->kind == FISHING_V4;
+  a.n_models = 0; a.reset_model = reset_model; a.model = soa.model;
+  if (p->kind == FISHING_V11) {
+    if (p->n_models < 1 || p->n_models > FISHING_MAX_MODELS) return FISHING_E_ARG;
+    a.n_models = p->n_models;
+  }
   a.mask = mask; a.reset_noise = reset_noise;
   a.state = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env; a.out_obs = out_obs;
   return (int)launch_reset(a, static_cast<cudaStream_t>(stream));
@@ -146,12 +195,22 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   a.state_in = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
   a.out_stock = out_stock; a.out_harvest = out_harvest;
+  a.gp = growth_of(p);
+  a.model = soa.model;
+  double any_sigma = 0.0;
+  if (int e = fill_table(p, &a.tab, &any_sigma)) return e;
+  if (p->kind == FISHING_V11) a.sigma = any_sigma;              // only steers "is any noise needed"
+  if (p->kind == FISHING_V10) {                                 // r <- r + alpha BEFORE the draw (growth_models.py:148)
+    volatile double r_next = p->r + p->alpha;
+    a.gp.r = r_next;
+  }
   // 16-byte vector path: every array that is accessed two-wide must be aligned to its pair size
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
              (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
              (!out_harvest || aligned(out_harvest, 16));
   if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
+  if (p->kind == FISHING_V11) vec = vec && aligned(soa.model, 8);
   if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
   if (vec && (p->flags & FISHING_PDL) && pdl_enabled()) a.flags |= STEP_FLAG_PDL;
   return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
@@ -183,6 +242,10 @@ int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint6
                           out_terminal ? out_terminal + off : nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
     cur.state = out_obs + off;
+    if (q.kind == FISHING_V10) {
+      volatile double r_next = q.r + q.alpha;
+      q.r = r_next;
+    }
   }
   if (T > 0 && n > 0 && cur.state != soa.state)
     return (int)cudaMemcpyAsync(soa.state, cur.state, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -240,6 +303,14 @@ int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const f
   a.out_return = r->out_return; a.out_done_step = r->out_done_step;
   a.trace_obs = r->trace_obs; a.trace_reward = r->trace_reward; a.trace_done = r->trace_done;
   a.trace_action = r->trace_action;
+  a.gp = growth_of(p);
+  a.alpha = p->alpha;
+  a.nonstationary = p->kind == FISHING_V10;
+  a.model = soa.model;
+  double any_sigma = 0.0;
+  if (int e = fill_table(p, &a.tab, &any_sigma)) return e;
+  if (p->kind == FISHING_V11) a.sigma = any_sigma;
+  if (m == 1 && p->kind == FISHING_V11 && !aligned(soa.model, 8)) return FISHING_E_ALIGN;
   return (int)launch_rollout(a, p->kind, r->policy, static_cast<cudaStream_t>(stream));
 }
 
@@ -263,6 +334,35 @@ int fishing_population_draw(const fishing_params* p, int64_t n, const void* x, i
   if (n == 0) return 0;
   return (int)launch_growth(p->kind, n, x, is_f32 != 0, p->r, p->K, p->C, p->sigma, z, out,
                             static_cast<cudaStream_t>(stream));
+}
+
+int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int64_t n, const double* x, const double* z,
+                               double* out, void* stream) {
+  if (!p || !is_lognormal(p->kind) || n < 0 || !x || !out) return FISHING_E_ARG;
+  if (!aligned(x, 8) || !aligned(out, 8) || (z && !aligned(z, 8))) return FISHING_E_ALIGN;
+  if (n == 0) return 0;
+  GrowthP g = growth_of(p);
+  int fn;
+  switch (p->kind) {
+    case FISHING_V5: fn = FISHING_FN_ALLEN; break;
+    case FISHING_V6: case FISHING_V10: fn = FISHING_FN_BEVERTON_HOLT; break;
+    case FISHING_V7: fn = FISHING_FN_MAY; break;
+    case FISHING_V8: fn = FISHING_FN_MYERS; break;
+    case FISHING_V9: fn = FISHING_FN_RICKER; break;
+    default: {
+      ModelTable t;
+      double any;
+      if (int e = fill_table(p, &t, &any)) return e;
+      if (model_index < 0 || model_index >= t.n_models) return FISHING_E_ARG;
+      fn = t.fn[model_index];
+      g = t.p[model_index];
+    }
+  }
+  if (p->kind == FISHING_V10) {
+    volatile double r_next = p->r + p->alpha;
+    g.r = r_next;
+  }
+  return (int)launch_growth_ln(fn, n, x, g, z, out, static_cast<cudaStream_t>(stream));
 }
 
 int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out) {
@@ -302,7 +402,7 @@ struct fishing_vec {
 
 static void vec_free(fishing_vec* v) {
   if (!v) return;
-  cudaFree(v->soa.state); cudaFree(v->soa.years); cudaFree(v->soa.K_env); cudaFree(v->soa.r_env);
+  cudaFree(v->soa.state); cudaFree(v->soa.years); cudaFree(v->soa.K_env); cudaFree(v->soa.r_env); cudaFree(v->soa.model);
   cudaFree(v->d_action); cudaFree(v->d_noise); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_terminal);
   for (int i = 0; i < 3; ++i) {
     if (v->streams[i]) cudaStreamDestroy(v->streams[i]);
@@ -328,6 +428,7 @@ int fishing_vec_create(const fishing_params* p, int64_t n, int64_t env_id0, int3
             cudaMalloc(&v->d_terminal, nd) == cudaSuccess;
   if (ok && p->kind == FISHING_V4)
     ok = cudaMalloc(&v->soa.K_env, nd) == cudaSuccess && cudaMalloc(&v->soa.r_env, nd) == cudaSuccess;
+  if (ok && p->kind == FISHING_V11) ok = cudaMalloc(&v->soa.model, (size_t)n * 4) == cudaSuccess;
   for (int i = 0; ok && i < 3; ++i)
     ok = cudaStreamCreateWithFlags(&v->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&v->ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -404,6 +505,7 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
     fishing_soa s = v->soa;
     s.state += off; s.years += off;
     if (s.K_env) { s.K_env += off; s.r_env += off; }
+    if (s.model) s.model += off;
     rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, noise ? v->d_noise + off : nullptr,
                       nullptr, s, v->d_obs + off, v->d_reward + off, v->d_done + off,
                       v->d_terminal + off, nullptr, nullptr, st);
@@ -420,6 +522,10 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
     if (e != cudaSuccess && rc == 0) rc = (int)e;
   }
   v->step_idx += 1;
+  if (v->p.kind == FISHING_V10) {
+    volatile double r_next = v->p.r + v->p.alpha;
+    v->p.r = r_next;
+  }
   return rc;
 }
 
@@ -450,6 +556,7 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
       fishing_soa s = v->soa;
       s.state += off; s.years += off;
       if (s.K_env) { s.K_env += off; s.r_env += off; }
+      if (s.model) s.model += off;
       rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, nullptr, nullptr, s, v->d_obs + off,
                         v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, st);
       if (rc) break;
@@ -460,6 +567,10 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
       if (e != cudaSuccess) rc = (int)e;
     }
     v->step_idx += 1;
+    if (v->p.kind == FISHING_V10) {
+      volatile double r_next = v->p.r + v->p.alpha;
+      v->p.r = r_next;
+    }
   }
   for (int i = 0; i < 3; ++i) {
     e = cudaStreamSynchronize(v->streams[i]);

@@ -8,7 +8,19 @@
 
 namespace fishing {
 
-enum Growth { LOGISTIC = 0, TIPPING = 1 };
+enum Growth { LOGISTIC = 0, TIPPING = 1,
+              // log-normal family (gym_fishing/envs/growth_models.py:208-261); G_MODEL picks one of them per environment
+              G_ALLEN = 2, G_BEVERTON_HOLT = 3, G_MYERS = 4, G_MAY = 5, G_RICKER = 6, G_MODEL = 7 };
+
+// growth-function parameters of the log-normal family (the reference's `params` dict) and the fishing-v11 model table
+struct GrowthP {
+  double r, K, C, M, theta, q, b, a, sigma;
+};
+struct ModelTable {
+  int32_t n_models;
+  int32_t fn[FISHING_MAX_MODELS];
+  GrowthP p[FISHING_MAX_MODELS];
+};
 // how r and K reach the kernel: shared scalars with K == 1 (the default; x/K and x*K are exact no-ops and are
 // skipped), shared scalars with general K, or per-environment arrays (fishing-v4).
 enum ParamMode { P_KONE = 0, P_UNIFORM = 1, P_PERENV = 2 };
@@ -72,6 +84,64 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
   }
 }
 
+// mu(x) of the five growth functions, growth_models.py:208-261, in the reference's evaluation order; log / pow / exp are
+// libdevice's (<= 1-2 ulp from numpy's), everything else one IEEE operation per reference operation.
+template <int FN>
+__device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
+  if (FN == FISHING_FN_ALLEN) {            // np.log(x) + r * (1 - x / K) * (1 - C) / K
+    const double y = __ddiv_rn(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))), __dsub_rn(1.0, g.C)), g.K);
+    return __dadd_rn(log(x), y);
+  } else if (FN == FISHING_FN_BEVERTON_HOLT) {
+    const double xc = (x < 0.0) ? 0.0 : x;                       // np.clip(x, 0, inf)
+    const double rc = (g.r < 0.0) ? 0.0 : g.r;
+    const double A = __dadd_rn(rc, 1.0);
+    const double B = __ddiv_rn((g.K < 0.0) ? 0.0 : g.K, rc);
+    return __dsub_rn(__dadd_rn(log(A), log(xc)), log(__dadd_rn(1.0, __ddiv_rn(xc, B))));
+  } else if (FN == FISHING_FN_MAY) {       // x + x*r*(1 - x/M) - a*x^q / (x^q + b^q), then log
+    const double xq = pow(x, g.q);
+    const double e = __dsub_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(x, g.r), __dsub_rn(1.0, __ddiv_rn(x, g.M)))),
+                               __ddiv_rn(__dmul_rn(g.a, xq), __dadd_rn(xq, pow(g.b, g.q))));
+    return log(e);
+  } else if (FN == FISHING_FN_MYERS) {     // log(r + 1) + theta*log(x) - log(1 + x^theta / M)
+    const double A = __dadd_rn(g.r, 1.0);
+    return __dsub_rn(__dadd_rn(log(A), __dmul_rn(g.theta, log(x))),
+                     log(__dadd_rn(1.0, __ddiv_rn(pow(x, g.theta), g.M))));
+  } else {                                 // Ricker: log(x) + r * (1 - x / K)
+    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))));
+  }
+}
+
+// np.maximum(0, np.random.lognormal(mu, sigma)) with the legacy generator's lognormal = exp(mu + sigma * gauss)
+template <int FN>
+__device__ __forceinline__ double grow_lognormal(double x1, const GrowthP& g, double z, bool noisy) {
+  double e = lognormal_mu<FN>(x1, g);
+  if (noisy) e = __dadd_rn(e, __dmul_rn(g.sigma, z));
+  const double v = exp(e);
+  return (0.0 > v) ? 0.0 : v;
+}
+
+__device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP& g, double z, bool noisy) {
+  switch (fn) {
+    case FISHING_FN_ALLEN: return grow_lognormal<FISHING_FN_ALLEN>(x1, g, z, noisy);
+    case FISHING_FN_BEVERTON_HOLT: return grow_lognormal<FISHING_FN_BEVERTON_HOLT>(x1, g, z, noisy);
+    case FISHING_FN_MYERS: return grow_lognormal<FISHING_FN_MYERS>(x1, g, z, noisy);
+    case FISHING_FN_MAY: return grow_lognormal<FISHING_FN_MAY>(x1, g, z, noisy);
+    default: return grow_lognormal<FISHING_FN_RICKER>(x1, g, z, noisy);
+  }
+}
+
+template <int GROWTH>
+__device__ __forceinline__ double grow_ln(double x1, const GrowthP& g, const ModelTable& tab, int model, double z,
+                                          bool noisy_uniform) {
+  if (GROWTH == G_ALLEN) return grow_lognormal<FISHING_FN_ALLEN>(x1, g, z, noisy_uniform);
+  if (GROWTH == G_BEVERTON_HOLT) return grow_lognormal<FISHING_FN_BEVERTON_HOLT>(x1, g, z, noisy_uniform);
+  if (GROWTH == G_MYERS) return grow_lognormal<FISHING_FN_MYERS>(x1, g, z, noisy_uniform);
+  if (GROWTH == G_MAY) return grow_lognormal<FISHING_FN_MAY>(x1, g, z, noisy_uniform);
+  if (GROWTH == G_RICKER) return grow_lognormal<FISHING_FN_RICKER>(x1, g, z, noisy_uniform);
+  // fishing-v11: the model (and its own sigma) belongs to the environment
+  return grow_by_model(tab.fn[model], x1, tab.p[model], z, true);
+}
+
 struct StepOut {
   double s2;      // next normalised state
   double reward;  // max(harvest, 0)
@@ -83,12 +153,16 @@ struct StepOut {
 // BaseFishingEnv.step body, base_fishing_env.py:60-81, for one environment given its quota.
 template <int GROWTH, int PM>
 __device__ __forceinline__ StepOut step_core(double s, double quota, double z, double r, double K, double C,
-                                             double sigma, bool noisy) {
+                                             double sigma, bool noisy, const GrowthP* gp = nullptr,
+                                             const ModelTable* tab = nullptr, int model = 0) {
+  // gp / tab are only dereferenced by the log-normal growth family (fishing-v5..v11)
   double x = __dadd_rn(s, 1.0);                     // get_fish_population :158-160
   if (PM != P_KONE) x = __dmul_rn(x, K);
   const double h = py_min(x, quota);                // harvest_draw :117
   const double x1 = py_max(__dsub_rn(x, h), 0.0);   // :118
-  const double x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
+  double x2;
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
+  else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);
   StepOut o;
   o.s2 = __dsub_rn(PM == P_KONE ? x2 : __ddiv_rn(x2, K), 1.0);  // get_state :162-164
   o.reward = py_max(h, 0.0);                        // :74

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dynamics.cuh"
+
 namespace fishing {
 
 // internal launch flag (upper bits of StepArgs::flags, never part of the public fishing_flags): use programmatic
@@ -33,6 +35,10 @@ struct StepArgs {
   double* __restrict__ out_terminal;
   double* __restrict__ out_stock;    // optional: fish_population after growth
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
+  // log-normal family (fishing-v5..v11)
+  GrowthP gp;
+  int32_t* model;                    // v11: per-env model index (updated at auto-reset)
+  ModelTable tab;                    // v11: the model table (by value in the kernel parameters)
 };
 
 struct ResetArgs {
@@ -40,6 +46,9 @@ struct ResetArgs {
   uint64_t epoch, seed;
   double s_reset, K_mean, r_mean, sigma_p;
   int32_t per_env;
+  int32_t n_models;                  // > 0: fishing-v11, draw / inject the model index
+  const int32_t* __restrict__ reset_model;
+  int32_t* model;
   const uint8_t* __restrict__ mask;
   const double* __restrict__ reset_noise;
   double* state;
@@ -72,6 +81,12 @@ struct RolloutArgs {
   double* __restrict__ trace_reward;
   uint8_t* __restrict__ trace_done;
   double* __restrict__ trace_action;
+  // log-normal family (fishing-v5..v11)
+  GrowthP gp;
+  double alpha;                      // v10: r += alpha before every draw
+  int32_t nonstationary;
+  int32_t* model;
+  ModelTable tab;
 };
 
 cudaError_t launch_step(const StepArgs& a, int kind, int act, bool vec, cudaStream_t st);
@@ -80,6 +95,8 @@ cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64
                               double* out, cudaStream_t st);
 cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r, double K, double C, double sigma,
                           double z, void* out, cudaStream_t st);
+cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
+                             cudaStream_t st);
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);
 int64_t reduce_scratch_doubles(int64_t n, int64_t groups);

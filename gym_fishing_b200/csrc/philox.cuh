@@ -151,6 +151,15 @@ __device__ __forceinline__ void sincospi_02(double t, double& sn, double& cs) {
   cs = b;
 }
 
+// Uniform integer in [0, n) from the first Philox word (fishing-v11 model draw, np.random.choice(models)):
+// floor(w0 * n / 2^32).
+__device__ __forceinline__ uint32_t uniform_index(uint64_t seed, uint64_t id, uint64_t t, uint32_t stream, uint32_t n) {
+  uint32_t w[4];
+  philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (stream << 24) | ((uint32_t)(t >> 32) & 0xFFFFFFu),
+                (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  return __umulhi(w[0], n);
+}
+
 __device__ __forceinline__ Normal2 normal_pair(uint64_t seed, uint64_t id, uint64_t t, uint32_t stream) {
   uint32_t w[4];
   philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (stream << 24) | ((uint32_t)(t >> 32) & 0xFFFFFFu),

@@ -77,7 +77,7 @@ __device__ __forceinline__ void store2_stream(T* base, const Lanes& L, T a, T b)
 
 struct EnvReg {
   double s, K, r, ret, S, quota_const;
-  int32_t years, done_step;
+  int32_t years, done_step, model;
   bool frozen;
 };
 
@@ -145,9 +145,10 @@ __device__ __forceinline__ void load_action_pair(const RolloutArgs& a, const Lan
 }
 
 template <int GROWTH, int PM>
-__device__ __forceinline__ void env_advance(const RolloutArgs& a, EnvReg& e, double quota, double z, bool noisy,
-                                            int64_t t, uint64_t gid, double& obs, double& reward, uint8_t& done) {
-  const StepOut o = step_core<GROWTH, PM>(e.s, quota, z, e.r, e.K, a.C, a.sigma, noisy);
+__device__ __forceinline__ void env_advance(const RolloutArgs& a, const GrowthP& gp, EnvReg& e, double quota, double z,
+                                            bool noisy, int64_t t, uint64_t gid, double& obs, double& reward,
+                                            uint8_t& done) {
+  const StepOut o = step_core<GROWTH, PM>(e.s, quota, z, e.r, e.K, a.C, a.sigma, noisy, &gp, &a.tab, e.model);
   e.years += 1;
   done = (e.years > a.Tmax) || o.dead;
   reward = o.reward;
@@ -164,6 +165,9 @@ __device__ __forceinline__ void env_advance(const RolloutArgs& a, EnvReg& e, dou
         e.K = v4_param(a.K_mean, a.sigma_p, d.z0);
         e.r = v4_param(a.r_mean, a.sigma_p, d.z1);
       }
+      if (GROWTH == G_MODEL)
+        e.model = (int32_t)uniform_index(a.seed, gid, a.step0 + (uint64_t)t, FISHING_STREAM_AUTORESET,
+                                         (uint32_t)a.tab.n_models);
       e.s = a.s_reset;
       obs = a.s_reset;
     } else if (a.flags & FISHING_FREEZE_DONE) {
@@ -218,7 +222,13 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
     e0.done_step = e1.done_step = -1;
     e0.frozen = e1.frozen = false;
     e0.quota_const = e1.quota_const = 0.0;
+    e0.model = e1.model = 0;
+    if (GROWTH == G_MODEL) {
+      const int2 md = load2<int2>(a.model, L);
+      e0.model = md.x; e1.model = md.y;
+    }
   }
+  GrowthP gp = a.gp;   // fishing-v10 lets r drift: r += alpha before every draw (growth_models.py:147-150)
   double act0 = 0.0, act1 = 0.0;
   if (POLICY == FISHING_POLICY_MSY && PM != P_PERENV) {
     e0.quota_const = policy_quota_msy<PM>(a, e0.K, act0);
@@ -228,6 +238,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 
   for (int64_t t = 0; t < a.T; ++t) {
     if (e0.frozen && e1.frozen && !tracing) break;
+    if (a.nonstationary) gp.r = __dadd_rn(gp.r, a.alpha);
     double z0 = 0.0, z1 = 0.0;
     if (ext_noise) {
       const double2 z = load2_stream<double2>(a.noise + t * a.n, L);
@@ -253,8 +264,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
     }
     double o0 = e0.s, o1 = e1.s, r0 = 0.0, r1 = 0.0;
     uint8_t d0 = 1, d1 = 1;
-    if (!e0.frozen) env_advance<GROWTH, PM>(a, e0, q0, z0, noisy, t, gid0, o0, r0, d0);
-    if (!e1.frozen) env_advance<GROWTH, PM>(a, e1, q1, z1, noisy, t, gid1, o1, r1, d1);
+    if (!e0.frozen) env_advance<GROWTH, PM>(a, gp, e0, q0, z0, noisy, t, gid0, o0, r0, d0);
+    if (!e1.frozen) env_advance<GROWTH, PM>(a, gp, e1, q1, z1, noisy, t, gid1, o1, r1, d1);
     if (tracing) {
       const int64_t off = t * a.n;
       if (a.trace_obs) store2_stream<double2>(a.trace_obs + off, L, o0, o1);
@@ -457,7 +468,31 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   return cudaGetLastError();
 }
 
+template <int GROWTH>
+static cudaError_t launch_rollout_ln(const RolloutArgs& a, int policy, cudaStream_t st) {
+  const int64_t threads = a.n >> 1;
+  const int block = 128;
+  const int64_t grid = (threads + block - 1) / block;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  switch (policy) {
+    case FISHING_POLICY_ACTIONS: rollout_kernel<GROWTH, P_UNIFORM, FISHING_POLICY_ACTIONS><<<(int)grid, block, 0, st>>>(a); break;
+    case FISHING_POLICY_ESCAPEMENT: rollout_kernel<GROWTH, P_UNIFORM, FISHING_POLICY_ESCAPEMENT><<<(int)grid, block, 0, st>>>(a); break;
+    default: rollout_kernel<GROWTH, P_UNIFORM, FISHING_POLICY_MSY><<<(int)grid, block, 0, st>>>(a); break;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st) {
+  switch (kind) {
+    case FISHING_V5: return launch_rollout_ln<G_ALLEN>(a, policy, st);
+    case FISHING_V6: case FISHING_V10: return launch_rollout_ln<G_BEVERTON_HOLT>(a, policy, st);
+    case FISHING_V7: return launch_rollout_ln<G_MAY>(a, policy, st);
+    case FISHING_V8: return launch_rollout_ln<G_MYERS>(a, policy, st);
+    case FISHING_V9: return launch_rollout_ln<G_RICKER>(a, policy, st);
+    case FISHING_V11: return launch_rollout_ln<G_MODEL>(a, policy, st);
+    default: break;
+  }
   if (kind == FISHING_V4) return launch_rollout_p<LOGISTIC, P_PERENV>(a, policy, st);
   const bool kone = a.K == 1.0;
   if (kind == FISHING_V2)

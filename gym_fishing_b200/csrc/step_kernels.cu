@@ -13,7 +13,7 @@ namespace fishing {
 // One environment: everything after the loads.  Returns the values to store.
 struct EnvResult {
   double obs, reward, K, r;
-  int32_t years;
+  int32_t years, model;
   uint8_t done;
   bool reset_fired;
   double terminal, stock, harvest;
@@ -21,10 +21,12 @@ struct EnvResult {
 
 template <int GROWTH, int PM, int ACT>
 __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, double s, typename ActT<ACT>::type act,
-                                             double z, bool noisy, int32_t years, double K, double r) {
+                                             double z, bool noisy, int32_t years, double K, double r,
+                                             int32_t model = 0) {
   const double quota = quota_of<PM, ACT>(act, a.n_actions, K);
-  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy);
+  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy, &a.gp, &a.tab, model);
   EnvResult e;
+  e.model = model;
   e.years = years + 1;                                   // base_fishing_env.py:75
   e.done = (e.years > a.Tmax) || o.dead;                 // :76-79
   e.obs = o.s2;
@@ -51,6 +53,9 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
       e.K = v4_param(a.K_mean, a.sigma_p, zK);
       e.r = v4_param(a.r_mean, a.sigma_p, zr);
     }
+    if (GROWTH == G_MODEL)                                // ModelUncertainty.reset, growth_models.py:197-204
+      e.model = (int32_t)uniform_index(a.seed, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET,
+                                       (uint32_t)a.tab.n_models);
     e.obs = a.s_reset;
   }
   return e;
@@ -103,8 +108,10 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
     rv = reinterpret_cast<const double2*>(a.r_env)[j];
   }
   const int64_t i0 = 2 * (int64_t)j;
-  const EnvResult e0 = advance<GROWTH, PM, ACT>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x);
-  const EnvResult e1 = advance<GROWTH, PM, ACT>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y);
+  int2 mdl = make_int2(0, 0);
+  if (GROWTH == G_MODEL) mdl = reinterpret_cast<const int2*>(a.model)[j];
+  const EnvResult e0 = advance<GROWTH, PM, ACT>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
+  const EnvResult e1 = advance<GROWTH, PM, ACT>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
   reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
   st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
   st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
       reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
       reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
     }
+    if (GROWTH == G_MODEL) reinterpret_cast<int2*>(a.model)[j] = make_int2(e0.model, e1.model);
   }
 }
 
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
     const double K = PM == P_PERENV ? a.K_env[i] : a.K;
     const double r = PM == P_PERENV ? a.r_env[i] : a.r;
     const EnvResult e = advance<GROWTH, PM, ACT>(a, i, a.state_in[i], reinterpret_cast<const AT*>(a.action)[i], z, noisy,
-                                                 a.years[i], K, r);
+                                                 a.years[i], K, r, GROWTH == G_MODEL ? a.model[i] : 0);
     a.out_obs[i] = e.obs;
     a.out_reward[i] = e.reward;
     a.out_done[i] = e.done;
@@ -157,6 +165,7 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
         a.K_env[i] = e.K;
         a.r_env[i] = e.r;
       }
+      if (GROWTH == G_MODEL) a.model[i] = e.model;
     }
   }
 }
@@ -182,6 +191,10 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs a) {
       a.K_env[i] = v4_param(a.K_mean, a.sigma_p, zK);
       a.r_env[i] = v4_param(a.r_mean, a.sigma_p, zr);
     }
+    if (a.n_models > 0)
+      a.model[i] = a.reset_model ? a.reset_model[i]
+                                 : (int32_t)uniform_index(a.seed, (uint64_t)(a.env_id0 + i), a.epoch, FISHING_STREAM_RESET,
+                                                          (uint32_t)a.n_models);
     a.state[i] = a.s_reset;
     a.years[i] = 0;
     if (a.out_obs) a.out_obs[i] = a.s_reset;
@@ -379,7 +392,23 @@ static cudaError_t launch_step_a(const StepArgs& a, int act, bool vec, cudaStrea
   }
 }
 
+// the log-normal family has Box actions only and always uses the general-K state scaling
+template <int GROWTH>
+static cudaError_t launch_step_ln(const StepArgs& a, int act, bool vec, cudaStream_t st) {
+  if (act == FISHING_ACT_F32) return launch_step_t<GROWTH, P_UNIFORM, FISHING_ACT_F32>(a, vec, st);
+  return launch_step_t<GROWTH, P_UNIFORM, FISHING_ACT_F64>(a, vec, st);
+}
+
 cudaError_t launch_step(const StepArgs& a, int kind, int act, bool vec, cudaStream_t st) {
+  switch (kind) {
+    case FISHING_V5: return launch_step_ln<G_ALLEN>(a, act, vec, st);
+    case FISHING_V6: case FISHING_V10: return launch_step_ln<G_BEVERTON_HOLT>(a, act, vec, st);
+    case FISHING_V7: return launch_step_ln<G_MAY>(a, act, vec, st);
+    case FISHING_V8: return launch_step_ln<G_MYERS>(a, act, vec, st);
+    case FISHING_V9: return launch_step_ln<G_RICKER>(a, act, vec, st);
+    case FISHING_V11: return launch_step_ln<G_MODEL>(a, act, vec, st);
+    default: break;
+  }
   if (kind == FISHING_V4) return launch_step_a<LOGISTIC, P_PERENV>(a, act, vec, st);
   const bool kone = a.K == 1.0;
   if (kind == FISHING_V2)
@@ -396,6 +425,21 @@ cudaError_t launch_reset(const ResetArgs& a, cudaStream_t st) {
 cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
                               double* out, cudaStream_t st) {
   noise_fill_kernel<<<grid_for(n * T, 256, 8), 256, 0, st>>>(seed, stream_id, n, env_id0, step0, T, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// stand-alone population_draw of the log-normal family on an array, ONE draw per element like np.random.lognormal(mu)
+__global__ void __launch_bounds__(256) growth_ln_kernel(int fn, int64_t n, const double* __restrict__ x, GrowthP gp,
+                                                         const double* __restrict__ z, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = grow_by_model(fn, x[i], gp, z ? z[i] : 0.0, true);
+}
+
+cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
+                             cudaStream_t st) {
+  growth_ln_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(fn, n, x, gp, z, out);
   count_launch();
   return cudaGetLastError();
 }

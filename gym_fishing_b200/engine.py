@@ -53,7 +53,9 @@ class EnvBatch:
     """
 
     def __init__(self, kind, n, *, device="cuda", env_id0=0, seed=0, auto_reset=False, r=0.3, K=1.0, sigma=0.0, C=0.5,
-                 x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1):
+                 x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1, **growth):
+        """**growth: extra entries of the reference's `params` dict for fishing-v5..v11 (growth_K, M, theta, q, b, a, alpha,
+        models=[(name, params), ...])."""
         torch = nat.require_cuda()
         nat.lib()
         self.torch = torch
@@ -69,12 +71,14 @@ class EnvBatch:
         self.step_idx = 0
         self.epoch = 0
         self.cfg = dict(r=r, K=K, sigma=sigma, C_=C, x0=x0, Tmax=Tmax, n_actions=n_actions, sigma_p=sigma_p, seed=seed)
+        self.cfg.update(growth)
         self.auto_reset = bool(auto_reset)
         f64 = dict(dtype=torch.float64, device=self.device)
         self.state = torch.empty(self.n, **f64)
         self.years = torch.zeros(self.n, dtype=torch.int32, device=self.device)
         self.K_env = torch.empty(self.n, **f64) if self.kind == nat.V4 else None
         self.r_env = torch.empty(self.n, **f64) if self.kind == nat.V4 else None
+        self.model = torch.zeros(self.n, dtype=torch.int32, device=self.device) if self.kind == nat.V11 else None
         self._scratch = None
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -86,12 +90,32 @@ class EnvBatch:
 
     def soa(self, state=None):
         s = self.state if state is None else state
-        return nat.FishingSoA(s.data_ptr(), self.years.data_ptr(), _ptr(self.K_env), _ptr(self.r_env))
+        return nat.FishingSoA(s.data_ptr(), self.years.data_ptr(), _ptr(self.K_env), _ptr(self.r_env), _ptr(self.model))
+
+    def _drift(self, steps):
+        """fishing-v10: r <- r + alpha before every draw (growth_models.py:147-150); sequential adds like the reference."""
+        if self.kind == nat.V10:
+            r, alpha = float(self.cfg["r"]), float(self.cfg.get("alpha", 0.0))
+            for _ in range(int(steps)):
+                r = r + alpha
+            self.cfg["r"] = r
 
     # ------------------------------------------------------------------------------------------------ kernels
-    def reset(self, mask=None, reset_noise=None, out_obs=None):
-        """fishing_reset.  mask: uint8/bool [n] selecting environments; reset_noise: [2, n] (zK, zr) for v4."""
+    def reset(self, mask=None, reset_noise=None, out_obs=None, reset_model=None):
+        """fishing_reset.  mask: uint8/bool [n] selecting environments; reset_noise: [2, n] (zK, zr) for v4;
+        reset_model: int32 [n] injected model indices for v11."""
         torch = self.torch
+        if reset_model is not None:
+            _chk_dev(reset_model, "reset_model", torch.int32, self.n)
+            if mask is not None:
+                mask = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+            p = self.params()
+            with torch.cuda.device(self.device):
+                rc = nat.lib().fishing_reset_models(ct.byref(p), self.n, self.env_id0, self.epoch, _ptr(mask),
+                                                    reset_model.data_ptr(), self.soa(), _ptr(out_obs), _stream(self.device))
+            nat.check(rc, "fishing_reset_models")
+            self.epoch += 1
+            return self.state
         if mask is not None:
             mask = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
             _chk_dev(mask, "mask", torch.uint8, self.n)
@@ -142,6 +166,7 @@ class EnvBatch:
                                     _ptr(out_stock), _ptr(out_harvest), torch.cuda.current_stream().cuda_stream)
         if rc:
             nat.check(rc, "fishing_step")
+        self._drift(1)
         self.step_idx += 1
         self.state = out_obs  # the newest observations ARE the state (no copy)
         return out_obs, out_reward, out_done
@@ -166,6 +191,7 @@ class EnvBatch:
                                              _ptr(noise), self.soa(), out_obs.data_ptr(), out_reward.data_ptr(),
                                              out_done.data_ptr(), _ptr(out_terminal), _stream(self.device))
         nat.check(rc, "fishing_step_many")
+        self._drift(T)
         self.step_idx += T
 
     def noise(self, T, *, stream=nat.STREAM_STEP, step0=None):
@@ -229,6 +255,7 @@ class EnvBatch:
         with torch.cuda.device(self.device):
             rc = nat.lib().fishing_rollout(ct.byref(p), self.n, self.env_id0, ct.byref(a), self.soa(), _stream(self.device))
         nat.check(rc, "fishing_rollout")
+        self._drift(T)
         self.step_idx += int(T)
         return out
 

@@ -124,7 +124,7 @@ class BaseFishingEnv(_EnvBase):
         s = self._slot
         per_env = self._kind == nat.V4
         return nat.FishingSoA(s.ptr(_O_STATE), s.ptr(_O_YEARS), s.ptr(_O_K) if per_env else None,
-                              s.ptr(_O_R) if per_env else None)
+                              s.ptr(_O_R) if per_env else None, None)
 
     def _draw(self):
         """One standard normal from numpy's global generator, looked up at call time like the reference does."""

@@ -26,7 +26,7 @@ def spec_ids():
 def make(id, **kwargs):
     if id not in _REGISTRY:
         raise KeyError(f"unknown environment id {id!r}; available: {spec_ids()} "
-                       "(fishing-v5..v11 of the reference are outside this engine's scope)")
+                       "(the reference has no fishing-v3)")
     entry_point, base = _REGISTRY[id]
     if callable(entry_point):
         cls = entry_point

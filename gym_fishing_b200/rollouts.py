@@ -8,7 +8,7 @@ from __future__ import annotations
 from . import _native as nat
 from .distributed import allreduce_stats, shard_range
 from .engine import EnvBatch
-from .vec_env import normalise_kwargs
+from .vec_env import growth_kwargs, normalise_kwargs
 
 
 def _rank_world():
@@ -39,7 +39,8 @@ def rollout_stats(env_id, num_envs, T, *, policy="escapement", S=None, msy_q=Non
     rank, world = _rank_world()
     lo, hi = shard_range(num_envs, rank, world, align=2)
     b = EnvBatch(kind, hi - lo, device=device, env_id0=lo, seed=seed, r=cfg["r"], K=cfg["K"], sigma=cfg["sigma"], C=cfg["C"],
-                 x0=cfg["x0"], Tmax=cfg["Tmax"], n_actions=cfg["n_actions"], sigma_p=cfg["sigma_p"])
+                 x0=cfg["x0"], Tmax=cfg["Tmax"], n_actions=cfg["n_actions"], sigma_p=cfg["sigma_p"],
+                 **growth_kwargs(kind, env_kwargs))
     b.reset()
     out = b.rollout(T, policy=policy, S=S, msy_q=msy_q, freeze_done=freeze_done)
     groups = 256 if (hi - lo) % 256 == 0 else 1          # fixed 256-wide tree: partition-invariant, see DESIGN.md section 7
@@ -79,7 +80,7 @@ def escapement_sweep(env_id="fishing-v1", *, levels=1024, replicates=16384, T=10
         S_levels = torch.as_tensor(S_levels, dtype=torch.float64, device=dev)
     S_env = S_levels.repeat(r_hi - r_lo).contiguous()
     b = EnvBatch(kind, n_local, device=dev, env_id0=r_lo * levels, seed=seed, r=cfg["r"], K=cfg["K"], sigma=cfg["sigma"],
-                 C=cfg["C"], x0=cfg["x0"], Tmax=cfg["Tmax"], sigma_p=cfg["sigma_p"])
+                 C=cfg["C"], x0=cfg["x0"], Tmax=cfg["Tmax"], sigma_p=cfg["sigma_p"], **growth_kwargs(kind, env_kwargs))
     b.reset()
     out = b.rollout(T, policy="escapement", S_env=S_env, noise_id_div=levels, freeze_done=True)
     local = b.reduce_stats(out["ret"], out["done_step"], groups=levels)

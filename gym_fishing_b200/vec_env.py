@@ -28,7 +28,50 @@ _CTOR_KEYS = {
     nat.V1: ("r", "K", "sigma", "init_state", "Tmax"),
     nat.V2: ("r", "K", "C", "sigma", "init_state", "Tmax"),
     nat.V4: ("K_mean", "r_mean", "price", "sigma", "sigma_p", "init_state", "Tmax"),
+    # log-normal growth family, gym_fishing/envs/growth_models.py:7-16,29-31,44-53,76-87,110-112,125-134,154-182
+    nat.V5: ("r", "K", "C", "sigma", "init_state", "Tmax"),
+    nat.V6: ("r", "K", "sigma", "init_state", "Tmax"),
+    nat.V7: ("r", "K", "M", "q", "b", "sigma", "a", "init_state", "Tmax"),
+    nat.V8: ("r", "K", "M", "theta", "sigma", "init_state", "Tmax"),
+    nat.V9: ("r", "K", "sigma", "init_state", "Tmax"),
+    nat.V10: ("r", "K", "sigma", "alpha", "init_state", "Tmax"),
+    nat.V11: ("models", "params", "Tmax"),
 }
+
+# constructor defaults of the log-normal family (same file:lines)
+_LN_DEFAULTS = {
+    nat.V5: dict(r=0.3, K=1, C=0.5, sigma=0.0, init_state=0.75),
+    nat.V6: dict(r=0.3, K=1, sigma=0.0, init_state=0.75),
+    nat.V7: dict(r=0.7, K=1.5, M=1.5, q=3, b=0.15, sigma=0.0, a=0.2, init_state=0.75),
+    nat.V8: dict(r=1.0, K=1.0, M=1.0, theta=3.0, sigma=0.0, init_state=1.5),
+    nat.V9: dict(r=0.3, K=1, sigma=0.0, init_state=0.75),
+    nat.V10: dict(r=0.8, K=1, sigma=0.0, alpha=-0.007, init_state=0.75),
+}
+V11_MODELS = ["allen", "beverton_holt", "myers", "may", "ricker"]
+V11_PARAMS = {
+    "allen": {"r": 0.3, "K": 1.0, "sigma": 0.0, "C": 0.5, "x0": 0.75},
+    "beverton_holt": {"r": 0.3, "K": 1, "sigma": 0.0, "x0": 0.75},
+    "myers": {"r": 1.0, "K": 1.0, "M": 1.0, "theta": 3.0, "sigma": 0.0, "x0": 1.5},
+    "may": {"r": 0.7, "K": 1.5, "M": 1.5, "q": 3, "b": 0.15, "sigma": 0.0, "a": 0.2, "x0": 0.75},
+    "ricker": {"r": 0.3, "K": 1, "sigma": 0.0, "x0": 0.75},
+}
+
+
+def growth_kwargs(kind, kw):
+    """Extra EnvBatch keyword arguments (`params`-dict entries) for fishing-v5..v11."""
+    if kind not in nat.LOGNORMAL_KINDS:
+        return {}
+    if kind == nat.V11:
+        models = list(kw.get("models", V11_MODELS))
+        params = kw.get("params", V11_PARAMS)
+        return dict(models=[(m, dict(params[m])) for m in models])
+    d = dict(_LN_DEFAULTS[kind])
+    d.update({k: v for k, v in kw.items() if k in d})
+    out = dict(growth_K=d["K"])
+    for k in ("M", "theta", "q", "b", "a", "alpha"):
+        if k in d:
+            out[k] = d[k]
+    return out
 
 
 def normalise_kwargs(kind, kw):
@@ -40,6 +83,17 @@ def normalise_kwargs(kind, kw):
     if bad:
         raise TypeError(f"unexpected keyword argument(s) {sorted(bad)} for this environment id")
     out = dict(r=0.3, K=1.0, sigma=0.0, C=0.5, x0=0.75, Tmax=100, n_actions=100, sigma_p=0.1)
+    if kind == nat.V11:      # base-class defaults scale the state whatever the model (growth_models.py:183-189)
+        out["Tmax"] = kw.get("Tmax", 100)
+        out["K"] = 1
+        return out
+    if kind in _LN_DEFAULTS:
+        d = dict(_LN_DEFAULTS[kind])
+        d.update({k: v for k, v in kw.items() if k in d})
+        out.update(r=d["r"], K=d["K"], sigma=d["sigma"], x0=d["init_state"], Tmax=kw.get("Tmax", 100))
+        if "C" in d:
+            out["C"] = d["C"]
+        return out
     if kind == nat.V4:
         out["r"] = kw.get("r_mean", 0.3)
         out["K"] = kw.get("K_mean", 1.0)
@@ -125,6 +179,7 @@ class FishingVecEnv:
         self.num_envs = int(num_envs)
         self.io = io
         self.cfg = normalise_kwargs(self.kind, env_kwargs)
+        self._growth = growth_kwargs(self.kind, env_kwargs)
         self.auto_reset = bool(auto_reset)
         self._seed = int(seed)
         self.env_id_offset = int(env_id_offset)
@@ -140,7 +195,8 @@ class FishingVecEnv:
             self.batch = EnvBatch(self.kind, self.num_envs, device=device, env_id0=self.env_id_offset, seed=seed,
                                   auto_reset=auto_reset, r=self.cfg["r"], K=self.cfg["K"], sigma=self.cfg["sigma"],
                                   C=self.cfg["C"], x0=self.cfg["x0"], Tmax=self.cfg["Tmax"],
-                                  n_actions=self.cfg["n_actions"], sigma_p=self.cfg["sigma_p"])
+                                  n_actions=self.cfg["n_actions"], sigma_p=self.cfg["sigma_p"],
+                                  **growth_kwargs(self.kind, env_kwargs))
             self.device = self.batch.device
             torch = self.batch.torch
             self._reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
@@ -159,7 +215,7 @@ class FishingVecEnv:
         c = self.cfg
         return nat.make_params(self.kind, r=c["r"], K=c["K"], sigma=c["sigma"], C_=c["C"], x0=c["x0"], Tmax=c["Tmax"],
                                n_actions=c["n_actions"], sigma_p=c["sigma_p"], seed=self._seed,
-                               flags=nat.AUTO_RESET if self.auto_reset else 0)
+                               flags=nat.AUTO_RESET if self.auto_reset else 0, **self._growth)
 
     def _create_handle(self):
         h = ct.c_void_p()

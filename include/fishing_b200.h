@@ -31,15 +31,33 @@
 extern "C" {
 #endif
 
-#define FISHING_ABI_VERSION 1
+#define FISHING_ABI_VERSION 2
 
 /* environment ids, gym_fishing/envs/__init__.py:17-35 */
 enum fishing_kind {
   FISHING_V0 = 0, /* FishingEnv, discrete actions         gym_fishing/envs/fishing_env.py:6-24        */
   FISHING_V1 = 1, /* FishingCtsEnv, Box actions           gym_fishing/envs/fishing_cts_env.py:4-12    */
   FISHING_V2 = 2, /* FishingTippingEnv                    gym_fishing/envs/fishing_tipping_env.py:6-35 */
-  FISHING_V4 = 4  /* FishingModelError, per-env r and K   gym_fishing/envs/fishing_model_error.py:6-48 */
+  FISHING_V4 = 4, /* FishingModelError, per-env r and K   gym_fishing/envs/fishing_model_error.py:6-48 */
+  /* "next row" f1 of SURVEY.md section 8: log-normal growth family, gym_fishing/envs/growth_models.py */
+  FISHING_V5 = 5,   /* Allen          growth_models.py:6-25,208-217   */
+  FISHING_V6 = 6,   /* BevertonHolt   growth_models.py:28-40,220-226  */
+  FISHING_V7 = 7,   /* May            growth_models.py:75-106,229-242 */
+  FISHING_V8 = 8,   /* Myers          growth_models.py:43-70,247-255  */
+  FISHING_V9 = 9,   /* Ricker         growth_models.py:109-121,258-261 */
+  FISHING_V10 = 10, /* NonStationary  growth_models.py:124-150 (Beverton-Holt with r += alpha before every draw) */
+  FISHING_V11 = 11  /* ModelUncertainty growth_models.py:153-204 (growth model drawn per env at every reset) */
 };
+
+/* growth functions of the log-normal family: x' = max(0, exp(mu(x) + sigma z)) */
+enum fishing_growth_fn { FISHING_FN_ALLEN = 0, FISHING_FN_BEVERTON_HOLT = 1, FISHING_FN_MYERS = 2, FISHING_FN_MAY = 3,
+                         FISHING_FN_RICKER = 4 };
+#define FISHING_MAX_MODELS 5
+
+/* the entries of the reference's `params` dict that a growth function reads (growth_models.py:208-261) */
+typedef struct fishing_growth_params {
+  double r, K, C, M, theta, q, b, a, sigma;
+} fishing_growth_params;
 
 enum fishing_action_dtype {
   FISHING_ACT_F64 = 0, /* Box action as float64 (the parity path)                                         */
@@ -92,6 +110,15 @@ typedef struct fishing_params {
   double x0;         /* init_state */
   double sigma_p;    /* v4 only */
   uint64_t seed;     /* Philox key */
+  /* ---- ABI v2: fishing-v5..v11.  For these ids `r`, `sigma`, `C` above and the fields below are the entries of the
+   * env's `params` dict, which is what the growth functions read; `K` stays the env ATTRIBUTE used to scale
+   * states/quotas and `growth_K` is params["K"] (the two are equal unless a caller changed one). */
+  double growth_K;
+  double M, theta, q, b, a; /* May: M q b a; Myers: M theta */
+  double alpha;             /* v10: r <- r + alpha before every population draw; `r` is the value BEFORE this step */
+  int32_t n_models;         /* v11: length of the `models` list (<= FISHING_MAX_MODELS) */
+  int32_t model_fn[FISHING_MAX_MODELS];                      /* v11: enum fishing_growth_fn of each list entry */
+  fishing_growth_params model_params[FISHING_MAX_MODELS];    /* v11: params[models[i]] */
 } fishing_params;
 
 /* Structure-of-arrays environment state (device pointers for the functions below). */
@@ -101,6 +128,7 @@ typedef struct fishing_soa {
   int32_t* years; /* [n] years_passed */
   double* K_env;  /* [n] v4 only, else NULL */
   double* r_env;  /* [n] v4 only, else NULL */
+  int32_t* model; /* [n] v11 only, else NULL: index into the `models` list, redrawn at every reset */
 } fishing_soa;
 
 int fishing_abi_version(void);
@@ -113,10 +141,14 @@ uint64_t fishing_launch_count(void);
  * reset -- BaseFishingEnv.reset (base_fishing_env.py:83-91), FishingModelError.reset / __init__ draws
  * (fishing_model_error.py:35-48).  `mask` (uint8[n], NULL = all) selects environments.  v4 draws K then r per
  * env from reset_noise[0..n) and reset_noise[n..2n) when given, else from Philox stream FISHING_STREAM_RESET
- * at counter `epoch`.  Writes soa.* and, if non-NULL, out_obs[n].
+ * at counter `epoch`.  v11 draws the model index (growth_models.py:200): from reset_model[n] (int32) when given, else
+ * floor(u * n_models) with u the first Philox word of the same stream.  Writes soa.* and, if non-NULL, out_obs[n].
  */
 int fishing_reset(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
                   const double* reset_noise, fishing_soa soa, double* out_obs, void* stream);
+/* same, with injected fishing-v11 model indices (int32[n]) */
+int fishing_reset_models(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t epoch, const uint8_t* mask,
+                         const int32_t* reset_model, fishing_soa soa, double* out_obs, void* stream);
 
 /*
  * step -- BaseFishingEnv.step (base_fishing_env.py:60-81) with get_quota (:135-147), get_fish_population
@@ -219,6 +251,11 @@ int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, d
  */
 int fishing_population_draw(const fishing_params* p, int64_t n, const void* x, int32_t is_f32, double z, void* out,
                             void* stream);
+
+/* the same for the log-normal growth family (fishing-v5..v11): float64 arrays, one draw z[i] PER ELEMENT (NULL = 0), the way
+ * np.random.lognormal(mu_array, sigma) draws (growth_models.py:217-261); model_index selects the fishing-v11 list entry */
+int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int64_t n, const double* x, const double* z,
+                               double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer front end: the engine owns device state; the caller passes ordinary host arrays (numpy, pinned

@@ -388,3 +388,82 @@ def unhex(h):
 
 
 __all__ = [n for n in dir() if not n.startswith("_")] + ["math"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# "next row" f1: the log-normal growth family fishing-v5..v9, v10 (non-stationary r) and v11 (model uncertainty),
+# gym_fishing/envs/growth_models.py:6-270.  Same step skeleton (base_fishing_env.py:60-81) with population_draw
+# replaced by x2 = max(0, lognormal(mu(x1), sigma)) = max(0, exp(mu + sigma*z)).  These functions read the env's
+# `params` DICT (growth_models.py:24,39,69,105,120), not the env attributes, so the attribute `sigma` that the policies
+# zero (policies.py:9-13,60-65) has no effect on them.
+# ----------------------------------------------------------------------------------------------------------------
+LN_KINDS = ("v5", "v6", "v7", "v8", "v9", "v10", "v11")
+MODEL_NAMES = ("allen", "beverton_holt", "myers", "may", "ricker")     # growth_models.py:156
+MODEL_OF_KIND = {"v5": "allen", "v6": "beverton_holt", "v7": "may", "v8": "myers", "v9": "ricker", "v10": "beverton_holt"}
+# constructor defaults, growth_models.py:7-16,29-31,44-53,76-87,110-112,125-134,157-179
+LN_DEFAULTS = {
+    "v5": dict(r=0.3, K=1, C=0.5, sigma=0.0, x0=0.75),
+    "v6": dict(r=0.3, K=1, sigma=0.0, x0=0.75),
+    "v7": dict(r=0.7, K=1.5, M=1.5, q=3, b=0.15, sigma=0.0, a=0.2, x0=0.75),
+    "v8": dict(r=1.0, K=1.0, M=1.0, theta=3.0, sigma=0.0, x0=1.5),
+    "v9": dict(r=0.3, K=1, sigma=0.0, x0=0.75),
+    "v10": dict(r=0.8, K=1, sigma=0.0, alpha=-0.007, x0=0.75),
+}
+V11_PARAMS = {
+    "allen": dict(r=0.3, K=1.0, sigma=0.0, C=0.5, x0=0.75),
+    "beverton_holt": dict(r=0.3, K=1, sigma=0.0, x0=0.75),
+    "myers": dict(r=1.0, K=1.0, M=1.0, theta=3.0, sigma=0.0, x0=1.5),
+    "may": dict(r=0.7, K=1.5, M=1.5, q=3, b=0.15, sigma=0.0, a=0.2, x0=0.75),
+    "ricker": dict(r=0.3, K=1, sigma=0.0, x0=0.75),
+}
+
+
+def lognormal_mu(model, x, p):
+    """mu(x) of the five growth functions, growth_models.py:208-261, one IEEE operation per line of the reference's
+    expression tree (np.log / np.power are the only non-exact operations)."""
+    x = np.asarray(x, dtype=F64)
+    with np.errstate(all="ignore"):
+        if model == "allen":                                   # :208-217
+            return np.log(x) + F64(p["r"]) * (1 - x / F64(p["K"])) * F64(1 - p["C"]) / F64(p["K"])
+        if model == "beverton_holt":                           # :220-226
+            xc = np.where(x < 0.0, 0.0, x)                     # np.clip(x, 0, inf); NaN stays
+            rc = F64(p["r"]) if p["r"] >= 0 else F64(0.0)
+            A = rc + 1
+            B = (F64(p["K"]) if p["K"] >= 0 else F64(0.0)) / rc
+            return np.log(A) + np.log(xc) - np.log(1 + xc / B)
+        if model == "may":                                     # :229-242
+            q = F64(p["q"])
+            xq = np.power(x, q)
+            e = x + x * F64(p["r"]) * (1 - x / F64(p["M"])) - F64(p["a"]) * xq / (xq + np.power(F64(p["b"]), q))
+            return np.log(e)
+        if model == "myers":                                   # :247-255
+            A = F64(p["r"]) + 1
+            th = F64(p["theta"])
+            return np.log(A) + th * np.log(x) - np.log(1 + np.power(x, th) / F64(p["M"]))
+        if model == "ricker":                                  # :258-261
+            return np.log(x) + F64(p["r"]) * (1 - x / F64(p["K"]))
+    raise ValueError(model)
+
+
+def grow_lognormal(model, x1, p, z):
+    """np.maximum(0, np.random.lognormal(mu, sigma)); the legacy generator computes exp(mu + sigma * gauss)."""
+    with np.errstate(all="ignore"):
+        mu = lognormal_mu(model, x1, p)
+        return np.maximum(0, np.exp(mu + F64(p["sigma"]) * np.asarray(z, dtype=F64)))
+
+
+def step_ln(model, s, action, z, years, p, *, K_state, Tmax=100):
+    """BaseFishingEnv.step with a log-normal growth model.  K_state is the env attribute K used by get_quota /
+    get_fish_population / get_state (for fishing-v11 it is the base default 1 whatever the model, growth_models.py:183-189)."""
+    s = np.asarray(s, dtype=F64)
+    K = F64(K_state)
+    with np.errstate(all="ignore"):
+        q = quota_from_action("v1", action, K)
+        x = population_from_state(s, K)
+        h, x1 = harvest(x, q)
+        x2 = grow_lognormal(model, x1, p, z)
+        s2 = state_from_population(x2, K)
+        reward = _py_max(h, 0.0)
+        years2 = np.asarray(years) + 1
+        done = (years2 > np.asarray(Tmax)) | (x2 <= 0.0)
+    return s2, reward, done, years2

@@ -38,14 +38,18 @@ import gym_fishing  # noqa: E402,F401  (the unmodified reference; registers the 
 from gym_fishing.models.policies import BMSY, escapement, msy  # noqa: E402
 
 _REAL_NORMAL = np.random.normal
+_REAL_LOGNORMAL = np.random.lognormal
+_REAL_CHOICE = np.random.choice
 
 
 class Injector:
     """Replaces numpy.random.normal; hands out loc + scale*Z[i] as Python floats, counting the calls."""
 
-    def __init__(self, z):
+    def __init__(self, z, choices=None):
         self.z = np.asarray(z, dtype=np.float64)
         self.i = 0
+        self.choices = choices
+        self.ci = 0
 
     def __call__(self, loc=0.0, scale=1.0, size=None):
         assert size is None
@@ -53,12 +57,36 @@ class Injector:
         self.i += 1
         return float(loc + scale * v)
 
+    def lognormal(self, mean=0.0, sigma=1.0, size=None):
+        """np.random.lognormal of the legacy generator is exp(mean + sigma * gauss) (one gauss per output element)."""
+        assert size is None
+        m = np.asarray(mean, dtype=np.float64)
+        if m.ndim == 0:
+            v = float(self.z[self.i])
+            self.i += 1
+            return float(np.exp(np.float64(float(m) + sigma * v)))
+        z = self.z[self.i:self.i + m.size].reshape(m.shape)
+        self.i += m.size
+        return np.exp(m + sigma * z)
+
+    def choice(self, a, size=None):
+        """np.random.choice(models) for fishing-v11: consumes the next entry of `choices`."""
+        assert size is None
+        v = a[self.choices[self.ci]]
+        self.ci += 1
+        return v
+
     def __enter__(self):
         np.random.normal = self
+        np.random.lognormal = self.lognormal
+        if getattr(self, "choices", None) is not None:
+            np.random.choice = self.choice
         return self
 
     def __exit__(self, *a):
         np.random.normal = _REAL_NORMAL
+        np.random.lognormal = _REAL_LOGNORMAL
+        np.random.choice = _REAL_CHOICE
 
 
 def hx(v):
@@ -342,6 +370,82 @@ def simulate_tables():
     return out
 
 
+# ------------------------------------------------------------------- next row f1: fishing-v5..v11 trajectories
+def trajectories_ln(kind, M, T, seed):
+    """Per-trajectory parameters for the log-normal growth family (growth_models.py).  v10 records the drifting r,
+    v11 the model drawn at construction and at the (single) reset."""
+    import copy
+
+    rng = np.random.default_rng(seed)
+    envid = "fishing-" + kind
+    names = ["r", "K", "C", "M", "theta", "q", "b", "a", "alpha", "sigma", "x0"]
+    P = {k: np.zeros(M) for k in names}
+    P["Tmax"] = np.zeros(M, dtype=np.int32)
+    P["model"] = np.zeros(M, dtype=np.int32)
+    A, NZ = np.zeros((T, M)), np.zeros((T, M))
+    OBS0, OBS, REW, DONE = np.zeros(M), np.zeros((T, M)), np.zeros((T, M)), np.zeros((T, M), dtype=np.uint8)
+    models = ["allen", "beverton_holt", "myers", "may", "ricker"]
+    for m in range(M):
+        default = m % 4 == 0
+        sigma = float(rng.choice([0.0, 0.02, 0.1]))
+        Tmax = int(rng.choice([7, 40, 1000]))
+        kw = dict(sigma=sigma, Tmax=Tmax)
+        if not default:
+            if kind in ("v5", "v6", "v9", "v10"):
+                kw.update(r=float(rng.uniform(0.1, 1.0)), K=float(rng.uniform(0.6, 3.0)))
+                kw["init_state"] = float(rng.uniform(0.1, 1.5)) * kw["K"]
+            if kind == "v5":
+                kw["C"] = float(rng.uniform(0.05, 0.9))
+            if kind == "v7":
+                kw.update(r=float(rng.uniform(0.3, 1.0)), K=float(rng.uniform(1.0, 2.0)), M=float(rng.uniform(1.0, 2.0)),
+                          q=int(rng.choice([2, 3, 4])), b=float(rng.uniform(0.1, 0.3)), a=float(rng.uniform(0.1, 0.3)),
+                          init_state=float(rng.uniform(0.2, 1.5)))
+            if kind == "v8":
+                kw.update(r=float(rng.uniform(0.5, 1.5)), K=float(rng.uniform(0.8, 1.5)), M=float(rng.uniform(0.5, 2.0)),
+                          theta=float(rng.choice([2.0, 2.5, 3.0])), init_state=float(rng.uniform(0.5, 2.0)))
+            if kind == "v10":
+                kw["alpha"] = float(rng.uniform(-0.01, 0.005))
+        if kind == "v11":
+            kw = dict(Tmax=Tmax, params=copy.deepcopy({k: dict(v) for k, v in {
+                "allen": {"r": 0.3, "K": 1.0, "sigma": sigma, "C": 0.5, "x0": 0.75},
+                "beverton_holt": {"r": 0.3, "K": 1, "sigma": sigma, "x0": 0.75},
+                "myers": {"r": 1.0, "K": 1.0, "M": 1.0, "theta": 3.0, "sigma": sigma, "x0": 1.5},
+                "may": {"r": 0.7, "K": 1.5, "M": 1.5, "q": 3, "b": 0.15, "sigma": sigma, "a": 0.2, "x0": 0.75},
+                "ricker": {"r": 0.3, "K": 1, "sigma": sigma, "x0": 0.75}}.items()}))
+        style = m % 3
+        acts = (rng.uniform(-1.0, -0.8, size=T) if style == 0 else rng.uniform(-1.0, 1.0, size=T) if style == 1
+                else rng.uniform(-1.3, -0.6, size=T))
+        z = rng.standard_normal(T)
+        choices = [int(rng.integers(0, 5)), int(rng.integers(0, 5))]
+        with Injector(np.zeros(4), choices=choices if kind == "v11" else None):
+            env = gym.make(envid, **kw)
+            if kind == "v10":
+                env.params = dict(env.params)   # undo the shared mutable default dict (growth_models.py:136-142 quirk)
+            obs = env.reset()
+        if kind == "v11":
+            P["model"][m] = models.index(env.model)
+            pp = env.params[env.model]
+        else:
+            pp = env.params
+        for k in names:
+            if k in pp:
+                P[k][m] = pp[k]
+        P["sigma"][m] = pp["sigma"]
+        P["Tmax"][m] = Tmax
+        P["K"][m] = pp["K"]
+        P["x0"][m] = env.init_state
+        OBS0[m] = obs[0]
+        A[:, m], NZ[:, m] = acts, z
+        for t in range(T):
+            with Injector(z[t:t + 1]) as inj:
+                obs, rew, done, _ = env.step(np.array([acts[t]]))
+                assert inj.i == 1
+            OBS[t, m], REW[t, m], DONE[t, m] = obs[0], rew, done
+    out = dict(actions=A, noise=NZ, obs0=OBS0, obs=OBS, reward=REW, done=DONE)
+    out.update({"p_" + k: v for k, v in P.items()})
+    return out
+
+
 def main():
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(kat(), f, indent=1)
@@ -349,6 +453,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"traj_{kind}.npz"), **trajectories(kind, 48, 160, 1000 + i))
         np.savez_compressed(os.path.join(HERE, f"autoreset_{kind}.npz"),
                             **trajectories(kind, 24, 160, 2000 + i, auto_reset=True))
+    for i, kind in enumerate(["v5", "v6", "v7", "v8", "v9", "v10", "v11"]):
+        np.savez_compressed(os.path.join(HERE, f"traj_{kind}.npz"), **trajectories_ln(kind, 24, 120, 3000 + i))
     with open(os.path.join(HERE, "policy.json"), "w") as f:
         json.dump(policy_table(), f, indent=1)
     with open(os.path.join(HERE, "simulate.json"), "w") as f:

@@ -29,16 +29,34 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/fishing_b200.h but not exported"
     assert sorted(nat.EXPORTS) == names
-    assert nat.lib().fishing_abi_version() == 1
+    assert nat.lib().fishing_abi_version() == nat.ABI_VERSION == 2
     assert b"bad argument" in nat.lib().fishing_error_string(-1)
 
 
-def test_struct_layouts_match_header_sizes():
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """Compile a C program against include/fishing_b200.h and compare sizes / offsets with the ctypes mirrors."""
     from gym_fishing_b200 import _native as nat
 
-    assert ctypes.sizeof(nat.FishingParams) == 4 * 4 + 6 * 8 + 8
-    assert ctypes.sizeof(nat.FishingSoA) == 32
-    assert ctypes.sizeof(nat.FishingRolloutArgs) == 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 6 * 8
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "fishing_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu ", sizeof(fishing_params), sizeof(fishing_soa), sizeof(fishing_rollout_args), sizeof(fishing_growth_params));
+  printf("%zu %zu %zu %zu %zu ", offsetof(fishing_params, seed), offsetof(fishing_params, growth_K), offsetof(fishing_params, alpha),
+         offsetof(fishing_params, n_models), offsetof(fishing_params, model_params));
+  printf("%zu %zu %zu\n", offsetof(fishing_rollout_args, S_env), offsetof(fishing_rollout_args, noise_id_div), offsetof(fishing_soa, model));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    P, S, R = nat.FishingParams, nat.FishingSoA, nat.FishingRolloutArgs
+    want = [ctypes.sizeof(P), ctypes.sizeof(S), ctypes.sizeof(R), ctypes.sizeof(nat.GrowthParams), P.seed.offset,
+            P.growth_K.offset, P.alpha.offset, P.n_models.offset, P.model_params.offset, R.S_env.offset,
+            R.noise_id_div.offset, S.model.offset]
+    assert got == want, (got, want)
 
 
 def test_no_cpu_fallback():
@@ -69,7 +87,7 @@ def test_registry_and_spaces():
     import gym_fishing_b200 as gf
     from gym_fishing_b200.spaces import Discrete, unit_box
 
-    assert gf.spec_ids() == ["fishing-v0", "fishing-v1", "fishing-v2", "fishing-v4"]
+    assert gf.spec_ids() == sorted(f"fishing-v{i}" for i in (0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11))
     with pytest.raises(KeyError):
         gf.make("fishing-v3")
     b = unit_box()
@@ -92,6 +110,13 @@ def test_ctor_kwargs_mapping():
         normalise_kwargs(nat.V1, dict(C=0.3))
     with pytest.raises(TypeError):
         normalise_kwargs(nat.V2, dict(n_actions=3))
+    from gym_fishing_b200.vec_env import growth_kwargs
+
+    c = normalise_kwargs(nat.V7, dict(sigma=0.1))
+    assert (c["r"], c["K"], c["x0"], c["sigma"]) == (0.7, 1.5, 0.75, 0.1)
+    g = growth_kwargs(nat.V7, dict(q=2))
+    assert (g["growth_K"], g["M"], g["q"], g["b"], g["a"]) == (1.5, 1.5, 2, 0.15, 0.2)
+    assert normalise_kwargs(nat.V11, {})["K"] == 1 and len(growth_kwargs(nat.V11, {})["models"]) == 5
 
 
 def test_lazy_infos():
@@ -158,7 +183,11 @@ print("ok", rank)
 def test_gloo_world2_sharding_and_stats(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER)
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+
+    with socket.socket() as sock:          # a port that is free right now
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script), ROOT]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)

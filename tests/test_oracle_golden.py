@@ -266,3 +266,30 @@ def test_scalar_port_equals_vectorised_oracle():
             s, r2, d2, years = fo.step_vec(kind, s, a if kind == "v0" else a[0], zz, years, r=r, K=K, sigma=0.05,
                                            C=0.3, n_actions=50, Tmax=40)
             assert close(obs[0], s, kind) and close(rew, r2, kind) and bool(d2) == done
+
+
+# ------------------------------------------------------------------------------------- next row f1: fishing-v5..v11
+def _ln_params(d, m, kind):
+    p = {k: float(d["p_" + k][m]) for k in ("r", "K", "C", "M", "theta", "q", "b", "a", "alpha", "sigma")}
+    return p
+
+
+@pytest.mark.parametrize("kind", ["v5", "v6", "v7", "v8", "v9", "v10", "v11"])
+def test_lognormal_family_trajectories_match_reference(kind):
+    d = np.load(os.path.join(G, f"traj_{kind}.npz"))
+    T, M = d["actions"].shape
+    for m in range(M):
+        p = _ln_params(d, m, kind)
+        model = fo.MODEL_NAMES[int(d["p_model"][m])] if kind == "v11" else fo.MODEL_OF_KIND[kind]
+        K_state = 1.0 if kind == "v11" else p["K"]
+        s, years = d["obs0"][m], 0
+        assert s == d["p_x0"][m] / K_state - 1
+        for t in range(T):
+            if kind == "v10":
+                p["r"] = p["r"] + p["alpha"]          # growth_models.py:148, before the draw, never reset
+            s, rew, done, years = fo.step_ln(model, s, d["actions"][t, m], d["noise"][t, m], years, p, K_state=K_state,
+                                             Tmax=int(d["p_Tmax"][m]))
+            assert np.isclose(s, d["obs"][t, m], rtol=1e-13, atol=1e-15, equal_nan=True), (kind, m, t, float(s), d["obs"][t, m])
+            assert np.isclose(rew, d["reward"][t, m], rtol=1e-13, atol=1e-15, equal_nan=True)
+            assert bool(done) == bool(d["done"][t, m]), (kind, m, t)
+    assert d["done"].any() and not d["done"].all()
