@@ -41,7 +41,7 @@ def timed(fn, dev, reps=3, warm=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg3,cfg4,cfg5")
+    ap.add_argument("--only", default="cfg3,cfg4,cfg5,f1")
     ap.add_argument("--per-gpu", action="store_true", help="keep the per-GPU share of the 8-GPU configuration")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every size by this factor (smoke runs)")
     args = ap.parse_args()
@@ -112,6 +112,30 @@ def main():
                       "ms": ms, "env_steps_per_s": levels * reps * 1000 / (ms * 1e-3), "best_S": float(res["S"][best]),
                       "best_mean_return": float(res["mean"][best]), "std_at_best": float(res["std"][best]),
                       "checksum_mean": float(res["mean"].sum())})
+
+    if "f1" in only:
+        # next-row f1: the log-normal growth family, K1 lock-step (step_many, PDL) and fused K2 with in-kernel escapement
+        from gym_fishing_b200.vec_env import growth_kwargs, normalise_kwargs
+
+        n, T = 1 << 20, 200
+        acts = torch.rand(T, n, dtype=torch.float64, device=dev) * 0.3 - 1.0
+        obs = torch.empty(T, n, dtype=torch.float64, device=dev)
+        rew = torch.empty_like(obs)
+        done = torch.empty(T, n, dtype=torch.uint8, device=dev)
+        for env_id in ("fishing-v5", "fishing-v6", "fishing-v7", "fishing-v8", "fishing-v9", "fishing-v10", "fishing-v11"):
+            kind = nat.KIND_OF_ID[env_id]
+            kw = dict(sigma=0.05, Tmax=100) if kind != nat.V11 else dict(Tmax=100)
+            cfg, gk = normalise_kwargs(kind, kw), growth_kwargs(kind, kw)
+            if kind == nat.V11:
+                gk["models"] = [(m, dict(p, sigma=0.05)) for m, p in gk["models"]]
+            b = EnvBatch(kind, n, device=dev, env_id0=rank * n, auto_reset=True, r=cfg["r"], K=cfg["K"], sigma=cfg["sigma"],
+                         C=cfg["C"], x0=cfg["x0"], Tmax=cfg["Tmax"], **gk)
+            b.reset()
+            ms1, _ = timed(lambda: b.step_many(acts, obs, rew, done), dev)
+            ms2, _ = timed(lambda: b.rollout(T, policy="escapement", S=0.5 * float(cfg["K"])), dev)
+            lines.append({"config": "f1", "env": env_id, "n_envs_per_gpu": n, "T": T, "n_gpus": world,
+                          "k1_env_steps_per_s": world * n * T / (ms1 * 1e-3), "k1_us_per_launch": ms1 * 1e3 / T,
+                          "k2_escapement_env_steps_per_s": world * n * T / (ms2 * 1e-3)})
 
     if rank == 0:
         for ln in lines:

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
     store2<double2>(a.K_env, L, e0.K, e1.K);
     store2<double2>(a.r_env, L, e0.r, e1.r);
   }
+  if (GROWTH == G_MODEL) store2<int2>(a.model, L, e0.model, e1.model);
   if (a.out_return) store2<double2>(a.out_return, L, e0.ret, e1.ret);
   if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
 }

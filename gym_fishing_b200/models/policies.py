@@ -17,6 +17,19 @@ def BMSY(env):
     """Stock size with maximum deterministic surplus production.  np.float32 for v0/v1/v2, np.float64 for v4,
     exactly as the reference returns it.  Resets the environment."""
     kind = env._kind
+    if kind in nat.LOGNORMAL_KINDS:
+        # fishing-v5..v11: no fused kernel; same procedure as the reference through the env's own (device) population_draw
+        grid = np.linspace(env.observation_space.low, env.observation_space.high, num=10001,
+                           dtype=env.observation_space.dtype)
+        x_0 = np.asarray([env.get_fish_population(g) for g in grid])
+        env.fish_population = x_0
+        keep = env.sigma
+        env.sigma = 0                      # no effect on these models (they read params["sigma"]), kept for fidelity
+        growth = env.population_draw() - x_0
+        env.sigma = keep
+        S = x_0[np.argmax(growth)]
+        env.reset()
+        return S
     K_f64 = kind == nat.V4 or isinstance(env.K, np.floating) or isinstance(env.r, np.floating)
     if getattr(env, "_noise_mode", "philox") == "numpy":
         env._draw()

@@ -446,6 +446,17 @@ def trajectories_ln(kind, M, T, seed):
     return out
 
 
+def policy_table_ln():
+    """BMSY / msy of the reference for the log-normal family at sigma = 0 (what upstream's own tests use)."""
+    rows = []
+    for envid in ("fishing-v5", "fishing-v6", "fishing-v7", "fishing-v8", "fishing-v9"):
+        with Injector(np.zeros(40000)):
+            env = gym.make(envid, sigma=0)
+            pol = msy(env)
+        rows.append(dict(env=envid, S=hx(pol.S), msy=hx(pol.msy), S_dtype=str(np.asarray(pol.S).dtype)))
+    return rows
+
+
 def main():
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(kat(), f, indent=1)
@@ -457,6 +468,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"traj_{kind}.npz"), **trajectories_ln(kind, 24, 120, 3000 + i))
     with open(os.path.join(HERE, "policy.json"), "w") as f:
         json.dump(policy_table(), f, indent=1)
+    with open(os.path.join(HERE, "policy_ln.json"), "w") as f:
+        json.dump(policy_table_ln(), f, indent=1)
     with open(os.path.join(HERE, "simulate.json"), "w") as f:
         json.dump(simulate_tables(), f, indent=1)
     np.save(os.path.join(HERE, "Z2024.npy"), Z)

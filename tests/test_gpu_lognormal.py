@@ -202,3 +202,23 @@ def test_scalar_api_lognormal_family_reproduces_reference_trajectories():
                 for t in range(T):
                     obs, r, dn, _ = env.step(np.array([d["actions"][t, m]]))
                     assert close(obs[0], d["obs"][t, m], 1.0) and close(r, d["reward"][t, m], 4.0) and dn == bool(d["done"][t, m]), (kind, m, t)
+
+
+def test_policies_on_the_lognormal_family():
+    """BMSY / msy through the env's device population_draw.  The reference evaluates mu in float32 with numpy's float32
+    log, this engine in float64, so S may land on a neighbouring grid point where the growth curve is flat: within two
+    grid steps, msy to 1e-5 relative."""
+    import json
+
+    import gym_fishing_b200 as gf
+
+    rows = json.load(open(os.path.join(G, "policy_ln.json")))
+    for row in rows:
+        env = gf.make(row["env"], sigma=0)
+        pol = gf.msy(env)
+        S_ref, q_ref = fo.unhex(row["S"]), fo.unhex(row["msy"])
+        assert isinstance(pol.S, np.float32)
+        assert abs(float(pol.S) - S_ref) <= 2 * (2.0 * env.K / 10000) + 1e-7, (row["env"], float(pol.S), S_ref)
+        assert abs(float(pol.msy) - q_ref) <= 1e-5 * abs(q_ref), (row["env"], float(pol.msy), q_ref)
+        df = env.simulate(gf.escapement(env))
+        assert len(df) == env.Tmax and df.reward.sum() > 0
