@@ -357,7 +357,8 @@ def run_gpu(args):
                          "traffic": traffic, "kernel": "step_kernel_vec2<LOGISTIC,P_KONE,F64>", "bytes_per_env_step": K1_BYTES,
                          "avg_launch_us": k1_us, "peak_source": peak_src},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * e2e_T, "d2h_bytes_per_step": n * 17 * e2e_T,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
+                    "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
                     "lock_steps_timed": e2e_T,
                     "api": "FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, 8 lock-steps per call)",
                     "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"}},

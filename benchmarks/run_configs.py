@@ -90,10 +90,16 @@ def main():
                 act_buf[t].copy_(a)                                                    # cast to fp64
                 venv.step_into(act_buf[t], obs_buf[t + 1], rew_buf[t], done_buf[t])
 
+        def env_only_c_loop():      # same kernels issued from C with programmatic dependent launch (no python per step)
+            obs_buf[0].copy_(venv.reset().view(-1))
+            venv.batch.step_many(fixed_actions, obs_buf[1:], rew_buf, done_buf)
+
         ms_env, _ = timed(env_only, dev)
+        ms_c, _ = timed(env_only_c_loop, dev)
         ms_pol, _ = timed(env_and_policy, dev)
         lines.append({"config": "cfg4", "env": "fishing-v4", "n_envs_per_gpu": n, "n_steps": n_steps, "n_gpus": world,
                       "ms_env_only": ms_env, "env_steps_per_s_env_only": world * n * n_steps / (ms_env * 1e-3),
+                      "ms_env_only_c_loop": ms_c, "env_steps_per_s_env_only_c_loop": world * n * n_steps / (ms_c * 1e-3),
                       "ms_env_plus_policy": ms_pol, "env_steps_per_s_env_plus_policy": world * n * n_steps / (ms_pol * 1e-3),
                       "bytes_per_env_step": 57, "done_rate_last": float(done_buf[-1].float().mean()),
                       "mean_reward_last": float(rew_buf[-1].mean())})

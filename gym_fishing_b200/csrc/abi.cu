@@ -232,11 +232,13 @@ int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint6
   bool alias = false;
   for (int i = 0; i < 2; ++i)
     for (int k = 0; k < 5; ++k) alias = alias || overlaps(ins[i], in_bytes[i], outs[k], out_bytes[k]);
-  if (alias) q.flags &= ~(uint32_t)FISHING_PDL;
-  else q.flags |= FISHING_PDL;
   fishing_soa cur = soa;
   for (int64_t t = 0; t < T; ++t) {
     const int64_t off = t * n;
+    // the first launch of a call is fully serialised behind whatever precedes it on the stream (its inputs might have
+    // been produced there); only launches that follow one of OUR launches of this call overlap with it
+    if (alias || t == 0) q.flags &= ~(uint32_t)FISHING_PDL;
+    else q.flags |= FISHING_PDL;
     int rc = fishing_step(&q, n, env_id0, step0 + (uint64_t)t, static_cast<const char*>(actions) + off * asz, action_dtype,
                           noise ? noise + off : nullptr, nullptr, cur, out_obs + off, out_reward + off, out_done + off,
                           out_terminal ? out_terminal + off : nullptr, nullptr, nullptr, stream);

@@ -25,6 +25,15 @@ static bool generic_only() {
   return on;
 }
 
+// FISHING_SWEEP_PLAIN=1 keeps sweeps on the one-pair-per-thread kernel (A/B checks of the amortised sweep kernel)
+static bool sweep_plain() {
+  static const bool on = [] {
+    const char* e = std::getenv("FISHING_SWEEP_PLAIN");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
+
 // The two environments a thread owns.  Default layout: adjacent ids (2j, 2j+1) -> 16-byte vector accesses.
 // Sweep layout (noise_id_div = m > 1, env id = replicate*m + level): thread = (replicate pair, level), i.e. ids
 // (2kp*m + j, (2kp+1)*m + j) -> two coalesced 8-byte accesses; both share the level and use the two halves of the
@@ -436,6 +445,73 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
   if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
 }
 
+// ------------------------------------------------------------------------------------------------ K2, sweep variant
+// Escapement grid sweep with common random numbers (noise_id_div = m = number of policy levels, env id =
+// replicate * m + level): the noise depends only on (replicate, step), so one thread that owns a replicate PAIR and LV
+// levels generates the pair's two normals once per step and applies them to 2*LV environments -- the Philox +
+// Box-Muller cost, more than half of the instructions of the plain kernel, is amortised LV times.  The levels of a thread
+// are strided by m/LV so that neighbouring threads touch neighbouring addresses.
+template <int GROWTH, int PM, bool NOISY, int LV>
+__global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = a.noise_id_div, mq = m / LV;
+  if (tid >= (a.n >> 1) / LV) return;
+  const int64_t kp = tid / mq, jq = tid - kp * mq;
+  const uint64_t noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
+  const bool auto_reset = a.flags & FISHING_AUTO_RESET;
+  const bool freeze = !auto_reset && (a.flags & FISHING_FREEZE_DONE);
+  FastEnv e[2 * LV];
+  int64_t idx[2 * LV];
+#pragma unroll
+  for (int l = 0; l < LV; ++l)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t i = (2 * kp + h) * m + jq + l * mq;
+      FastEnv& v = e[2 * l + h];
+      idx[2 * l + h] = i;
+      v.s = a.state[i];
+      v.years = a.years[i];
+      v.K = PM == P_PERENV ? a.K_env[i] : a.K;
+      v.r = PM == P_PERENV ? a.r_env[i] : a.r;
+      v.S = a.S_env ? a.S_env[i] : a.S;
+      v.ret = 0.0;
+      v.done_step = -1;
+      v.frozen = false;
+      v.quota_const = 0.0;
+    }
+  const int T = (int)a.T;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    double z[2] = {0.0, 0.0};
+    if (NOISY) {
+      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      z[0] = d.z0;
+      z[1] = d.z1;
+    }
+    bool all_frozen = freeze;
+#pragma unroll
+    for (int k = 0; k < 2 * LV; ++k) {
+      if (!e[k].frozen)
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY>(a, e[k], 0.0, z[k & 1], t, (uint64_t)(a.env_id0 + idx[k]),
+                                                                     auto_reset, freeze);
+      all_frozen = all_frozen && e[k].frozen;
+    }
+    if (all_frozen) break;
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * LV; ++k) {
+    const int64_t i = idx[k];
+    a.state[i] = e[k].s;
+    a.years[i] = e[k].years;
+    if (PM == P_PERENV) {
+      a.K_env[i] = e[k].K;
+      a.r_env[i] = e[k].r;
+    }
+    if (a.out_return) a.out_return[i] = e[k].ret;
+    if (a.out_done_step) a.out_done_step[i] = e[k].done_step;
+  }
+}
+
 template <int GROWTH, int PM, int POLICY>
 static void launch_fast_n(const RolloutArgs& a, bool noisy, int grid, int block, cudaStream_t st) {
   if (noisy) rollout_fast_kernel<GROWTH, PM, POLICY, true><<<grid, block, 0, st>>>(a);
@@ -451,7 +527,12 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   const bool tracing = a.trace_obs || a.trace_reward || a.trace_done || a.trace_action;
   const bool fast = !a.discrete && !tracing && !a.noise && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
-  if (fast) {
+  constexpr int SWEEP_LV = 4;
+  if (fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && a.noise_id_div % SWEEP_LV == 0 && !sweep_plain()) {
+    const int64_t sgrid = (threads / SWEEP_LV + block - 1) / block;
+    if (a.sigma != 0.0) rollout_sweep_kernel<GROWTH, PM, true, SWEEP_LV><<<(int)sgrid, block, 0, st>>>(a);
+    else rollout_sweep_kernel<GROWTH, PM, false, SWEEP_LV><<<(int)sgrid, block, 0, st>>>(a);
+  } else if (fast) {
     const bool noisy = a.sigma != 0.0;
     switch (policy) {
       case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, (int)grid, block, st); break;

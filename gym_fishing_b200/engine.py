@@ -45,6 +45,20 @@ def _chk_dev(t, name, dtype=None, n=None):
         raise ValueError(f"{name} must have {n} elements, got {t.numel()}")
 
 
+class _Cfg(dict):
+    """dict that counts its mutations, so that the ctypes parameter block is rebuilt only when something changed."""
+
+    version = 0
+
+    def __setitem__(self, k, v):
+        self.version += 1
+        super().__setitem__(k, v)
+
+    def update(self, *a, **kw):
+        self.version += 1
+        super().update(*a, **kw)
+
+
 class EnvBatch:
     """Structure-of-arrays state of `n` environments on one GPU plus the kernels that advance it.
 
@@ -70,8 +84,9 @@ class EnvBatch:
         self.env_id0 = int(env_id0)
         self.step_idx = 0
         self.epoch = 0
-        self.cfg = dict(r=r, K=K, sigma=sigma, C_=C, x0=x0, Tmax=Tmax, n_actions=n_actions, sigma_p=sigma_p, seed=seed)
+        self.cfg = _Cfg(r=r, K=K, sigma=sigma, C_=C, x0=x0, Tmax=Tmax, n_actions=n_actions, sigma_p=sigma_p, seed=seed)
         self.cfg.update(growth)
+        self._p_cache = (None, None, None)
         self.auto_reset = bool(auto_reset)
         f64 = dict(dtype=torch.float64, device=self.device)
         self.state = torch.empty(self.n, **f64)
@@ -83,10 +98,17 @@ class EnvBatch:
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def params(self, **override):
+        if not override:
+            ver, auto, p = self._p_cache
+            if ver == self.cfg.version and auto == self.auto_reset:
+                return p
         cfg = dict(self.cfg)
         cfg.update(override)
         flags = cfg.pop("flags", nat.AUTO_RESET if self.auto_reset else 0)
-        return nat.make_params(self.kind, flags=flags, **cfg)
+        p = nat.make_params(self.kind, flags=flags, **cfg)
+        if not override:
+            self._p_cache = (self.cfg.version, self.auto_reset, p)
+        return p
 
     def soa(self, state=None):
         s = self.state if state is None else state
