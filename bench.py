@@ -156,6 +156,30 @@ def cpu_vectorised_throughput(n=1 << 20, T=8):
     return n * T / (time.perf_counter() - t0)
 
 
+def cpu_c_port_throughput(n=1 << 20, T=16):
+    """Best-a-CPU-can-do line: the C restatement (oracle/fishing_oracle.c, -O2, OpenMP over all cores, no FMA)."""
+    import numpy as np
+
+    try:
+        from oracle.build_c import load
+
+        lib = load()
+    except Exception:  # noqa: BLE001
+        return None
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-1, 1, size=(T, n))
+    z = rng.standard_normal((T, n))
+    s = np.full(n, CFG["x0"] / CFG["K"] - 1)
+    years = np.zeros(n, dtype=np.int32)
+    rew, done = np.zeros(n), np.zeros(n, dtype=np.uint8)
+    args = (1, n, T, CFG["r"], CFG["K"], CFG["sigma"], 0.5, 100.0, CFG["Tmax"], CFG["x0"] / CFG["K"] - 1, a.ctypes.data, z.ctypes.data,
+            s.ctypes.data, years.ctypes.data, rew.ctypes.data, done.ctypes.data)
+    lib.oracle_rollout(*args)
+    t0 = time.perf_counter()
+    lib.oracle_rollout(*args)
+    return n * T / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
     to the GPU box, so this times the oracle's reference-shaped scalar port (same numpy-scalar operations per step,
@@ -348,7 +372,10 @@ def run_gpu(args):
             v1 = cpu_port_throughput(args.cpu_steps, 1)
             cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_steps} env.step calls of the reference-shaped scalar port (oracle.ScalarPortEnv), fishing-v1 sigma=0.01",
-                   "numpy_vectorised_1core": cpu_vectorised_throughput()}
+                   "numpy_vectorised_1core": cpu_vectorised_throughput(),
+                   "c_openmp_all_cores": cpu_c_port_throughput(), "host_cores": os.cpu_count(),
+                   "note": "value = the reference-shaped port (what the reference itself achieves per core); the numpy-vectorised and "
+                           "C/OpenMP figures are best-effort CPU restatements with pre-generated noise, for context"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
