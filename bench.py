@@ -175,9 +175,12 @@ def cpu_c_port_throughput(n=1 << 20, T=16):
     args = (1, n, T, CFG["r"], CFG["K"], CFG["sigma"], 0.5, 100.0, CFG["Tmax"], CFG["x0"] / CFG["K"] - 1, a.ctypes.data, z.ctypes.data,
             s.ctypes.data, years.ctypes.data, rew.ctypes.data, done.ctypes.data)
     lib.oracle_rollout(*args)
-    t0 = time.perf_counter()
-    lib.oracle_rollout(*args)
-    return n * T / (time.perf_counter() - t0)
+    best = 0.0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        lib.oracle_rollout(*args)
+        best = max(best, n * T / (time.perf_counter() - t0))
+    return best
 
 
 def run_reference(args):
