@@ -106,3 +106,56 @@ def plot_policyfn(self, df, output="policy.png"):
         plt.plot(g.state, g.state - g.action, color="blue")
     plt.savefig(output)
     plt.close("all")
+
+
+def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=None, noise=None, seed=0, device="cuda",
+                       **env_kwargs):
+    """simulate_mdp (shared_env.py:29-54) for one of the built-in policies with ALL repetitions run as one fused rollout on
+    the device: `reps` environments, at most Tmax steps, an environment stops at its first done (the `break` at :51).
+    Returns the same table [time, state, action, reward, rep] (same one-step lag of the quota / reward columns).
+
+    policy: "escapement" (S = BMSY by default) or "msy" (msy_q = surplus production at BMSY by default);
+    noise: optional [Tmax, reps] standard normals to inject (else the engine's Philox stream keyed by `seed`)."""
+    import torch
+
+    from . import _native as nat
+    from .engine import EnvBatch, bmsy
+    from .vec_env import growth_kwargs, normalise_kwargs
+
+    kind = nat.KIND_OF_ID[env_id]
+    cfg = normalise_kwargs(kind, env_kwargs)
+    if kind in nat.LOGNORMAL_KINDS and (S is None and msy_q is None):
+        raise ValueError("pass S / msy_q for fishing-v5..v11 (use models.policies.BMSY(env) on a scalar env)")
+    if S is None or (policy == "msy" and msy_q is None):
+        S0, q0 = bmsy(kind, r=cfg["r"], K=cfg["K"], C=cfg["C"], K_is_f64=(kind == nat.V4))
+        S = S0 if S is None else S
+        msy_q = q0 if msy_q is None else msy_q
+    n = int(reps) + (int(reps) & 1)          # the fused kernel owns environments in pairs
+    T = int(cfg["Tmax"])
+    b = EnvBatch(kind, n, device=device, seed=seed, r=cfg["r"], K=cfg["K"], sigma=cfg["sigma"], C=cfg["C"], x0=cfg["x0"],
+                 Tmax=T, n_actions=cfg["n_actions"], sigma_p=cfg["sigma_p"], **growth_kwargs(kind, env_kwargs))
+    b.reset()
+    obs0 = b.state.clone()
+    K = b.K_env.clone() if b.K_env is not None else torch.full((n,), float(cfg["K"]), dtype=torch.float64, device=b.device)
+    if noise is not None:
+        z = torch.zeros((T, n), dtype=torch.float64, device=b.device)
+        z[:, :reps] = torch.as_tensor(np.asarray(noise, dtype=np.float64), device=b.device).reshape(T, reps)
+        noise = z
+    out = b.rollout(T, policy=policy, S=float(S), msy_q=None if msy_q is None else float(msy_q), noise=noise,
+                    freeze_done=True, trace=True, trace_action=True)
+    obs, rew, act = out["obs"].cpu().numpy(), out["reward"].cpu().numpy(), out["action"].cpu().numpy()
+    dstep = out["done_step"].cpu().numpy()
+    obs0, K = obs0.cpu().numpy(), K.cpu().numpy()
+    chunks = []
+    for rep in range(int(reps)):
+        L = T if dstep[rep] < 0 else int(dstep[rep]) + 1           # steps actually taken
+        s_before = np.concatenate([[obs0[rep]], obs[:L - 1, rep]])
+        a_prev = act[:L - 1, rep]
+        if kind == nat.V0:
+            quota = (a_prev / cfg["n_actions"]) * K[rep]
+        else:
+            quota = (np.clip(a_prev, -1.0, 1.0) + 1) * K[rep]
+        chunks.append(np.column_stack([np.arange(L), (s_before + 1) * K[rep], np.concatenate([[0.0], quota]),
+                                       np.concatenate([[0.0], rew[:L - 1, rep]]), np.full(L, rep)]))
+    df = DataFrame(np.concatenate(chunks), columns=COLUMNS)
+    return df.astype({"time": int, "rep": int})

@@ -190,3 +190,46 @@ def test_step_many_host_pipeline_equals_per_step_calls():
     assert done.sum() > n
     for v in (a, b, c):
         v.close()
+
+
+def test_fused_simulate_matches_the_reference_simulate_tables():
+    """simulate_mdp_fused (one K2 launch for all repetitions) against tests/golden/simulate.json (recorded from the
+    reference's env.simulate) with the reference's noise injected, and against the host-loop simulate_mdp."""
+    import json
+    import os
+
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.shared_env import simulate_mdp_fused
+
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    Z = np.load(os.path.join(G, "Z2024.npy"))
+    tabs = json.load(open(os.path.join(G, "simulate.json")))
+    checked = 0
+    for tab in tabs:
+        if tab["policy"] != "escapement":
+            continue     # the msy tables use float32 actions (numpy promotion of the float32 msy constant); host loop covers them
+        kind = "v" + tab["env"].split("-v")[1]
+        z = Z[tab["noise_offset"] + 1:]            # BMSY consumed one draw
+        ref = tab["rows"]
+        reps = tab["reps"]
+        # the reference consumes one draw per executed step, repetition after repetition
+        lens = [sum(1 for r in ref if r[4] == rep) for rep in range(reps)]
+        Tmax = 100
+        noise = np.zeros((Tmax, reps))
+        pos = 0
+        for rep, L in enumerate(lens):
+            noise[:L, rep] = z[pos:pos + L]
+            pos += L
+        df = simulate_mdp_fused(tab["env"], "escapement", reps, noise=noise, **tab["kw"])
+        assert len(df) == len(ref)
+        for mine, r in zip(df.values.tolist(), ref):
+            assert int(mine[0]) == r[0] and int(mine[4]) == r[4]
+            for j in (1, 2, 3):
+                rv = fo.unhex(r[j])
+                assert abs(mine[j] - rv) <= (1e-12 if kind == "v2" else 0.0) * max(1.0, abs(rv)), (tab["env"], mine, r)
+        checked += 1
+    assert checked >= 2
+    # Philox noise, many repetitions: shapes and the lag convention
+    df = simulate_mdp_fused("fishing-v1", "msy", 1001, sigma=0.05, Tmax=30)
+    assert df.rep.max() == 1000 and (df[df.time == 0].action == 0).all() and (df[df.time == 0].reward == 0).all()
+    assert df.groupby("rep").time.max().max() == 29
