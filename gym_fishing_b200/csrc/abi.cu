@@ -196,6 +196,7 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
   a.out_stock = out_stock; a.out_harvest = out_harvest;
   a.gp = growth_of(p);
+  a.keys = philox_round_keys(p->seed);
   a.model = soa.model;
   double any_sigma = 0.0;
   if (int e = fill_table(p, &a.tab, &any_sigma)) return e;

@@ -159,7 +159,9 @@ __device__ __forceinline__ StepOut step_core(double s, double quota, double z, d
   double x = __dadd_rn(s, 1.0);                     // get_fish_population :158-160
   if (PM != P_KONE) x = __dmul_rn(x, K);
   const double h = py_min(x, quota);                // harvest_draw :117
-  const double x1 = py_max(__dsub_rn(x, h), 0.0);   // :118
+  // :118 max(x - h, 0.0) is the identity: h = min(x, quota) <= x (or h = x when the quota is NaN), so x - h is +0, a
+  // positive number or NaN for every input, and Python's max(v, 0.0) returns v in all three cases
+  const double x1 = __dsub_rn(x, h);
   double x2;
   if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
   else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);

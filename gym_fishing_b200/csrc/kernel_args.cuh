@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "dynamics.cuh"
+#include "philox.cuh"
 
 namespace fishing {
 
@@ -37,6 +38,7 @@ struct StepArgs {
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
+  PhiloxKeys keys;                   // round keys of `seed`
   int32_t* model;                    // v11: per-env model index (updated at auto-reset)
   ModelTable tab;                    // v11: the model table (by value in the kernel parameters)
 };

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
     if (ext_noise) {
       z = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
     } else if (noisy) {
-      const Normal2 d = normal_pair(a.seed, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
       z = make_double2(d.z0, d.z1);
     }
   }
