@@ -94,6 +94,28 @@ static bool pdl_enabled() {
   return on;
 }
 
+// device-side address of a page-locked host allocation (NULL if the pointer is ordinary pageable memory)
+static void* device_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
+// FISHING_VEC_ZEROCOPY=1 opts in to the zero-copy path of the host front end.  Measured on the B200 box it is not faster
+// than the staged copy-engine pipeline (2.46e9 vs 2.54e9 env-steps/s): both sit at the PCIe limit of ~45 GB/s per
+// direction under bidirectional load, so the staged path stays the default.
+static bool zero_copy_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("FISHING_VEC_ZEROCOPY");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 static bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
   if (!a || !b) return false;
   const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b);
@@ -169,10 +191,23 @@ static int reset_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint6
   return (int)launch_reset(a, static_cast<cudaStream_t>(stream));
 }
 
+static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                     int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
+                     double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
+                     double* out_obs2, void* stream);
+
 int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                  int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                  double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
                  void* stream) {
+  return step_impl(p, n, env_id0, step_idx, action, action_dtype, noise, reset_noise, soa, out_obs, out_reward, out_done,
+                   out_terminal, out_stock, out_harvest, nullptr, stream);
+}
+
+static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                     int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
+                     double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
+                     double* out_obs2, void* stream) {
   if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind) || !action || !out_obs || !out_reward || !out_done)
     return FISHING_E_ARG;
   const int asz = act_size(action_dtype);
@@ -195,6 +230,7 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   a.state_in = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
   a.out_stock = out_stock; a.out_harvest = out_harvest;
+  a.out_obs2 = out_obs2;
   a.gp = growth_of(p);
   a.keys = philox_round_keys(p->seed);
   a.model = soa.model;
@@ -209,7 +245,7 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
              (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
-             (!out_harvest || aligned(out_harvest, 16));
+             (!out_harvest || aligned(out_harvest, 16)) && (!out_obs2 || aligned(out_obs2, 16));
   if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
   if (p->kind == FISHING_V11) vec = vec && aligned(soa.model, 8);
   if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
@@ -541,6 +577,35 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
   if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
   cudaError_t e = cudaSetDevice(v->device);
   if (e != cudaSuccess) return (int)e;
+  // Zero-copy mode: when every host array is page-locked (fishing_host_alloc / cudaHostRegister) the kernel reads the
+  // actions and writes observations / rewards / dones straight over PCIe, one launch per lock-step with programmatic
+  // dependent launch between them -- no staging copies, no copy-engine round trips.
+  {
+    void* d_act = device_alias(actions);
+    void* d_obs = device_alias(obs_out);
+    void* d_rew = device_alias(reward_out);
+    void* d_done = device_alias(done_out);
+    if (d_act && d_obs && d_rew && d_done && zero_copy_enabled()) {
+      cudaStream_t st = v->streams[0];
+      fishing_params q = v->p;
+      int rc = 0;
+      for (int64_t t = 0; t < T && rc == 0; ++t) {
+        q.flags = (v->p.flags & ~(uint32_t)FISHING_PDL) | (t > 0 ? (uint32_t)FISHING_PDL : 0u);
+        rc = step_impl(&q, v->n, v->env_id0, v->step_idx, static_cast<const char*>(d_act) + t * v->n * asz, action_dtype, nullptr,
+                       nullptr, v->soa, v->soa.state, static_cast<double*>(d_rew) + t * v->n,
+                       static_cast<uint8_t*>(d_done) + t * v->n, v->d_terminal, nullptr, nullptr,
+                       static_cast<double*>(d_obs) + t * v->n, st);
+        v->step_idx += 1;
+        if (q.kind == FISHING_V10) {
+          volatile double r_next = q.r + q.alpha;
+          q.r = r_next;
+          v->p.r = r_next;
+        }
+      }
+      e = cudaStreamSynchronize(st);
+      return rc ? rc : (int)e;
+    }
+  }
   // a fixed chunk -> stream assignment keeps every dependency (state, staging buffers) inside one in-order stream;
   // the three streams keep an H2D, a kernel and a D2H of different chunks in flight at the same time
   const int64_t n = v->n;

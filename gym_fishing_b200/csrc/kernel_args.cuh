@@ -36,6 +36,8 @@ struct StepArgs {
   double* __restrict__ out_terminal;
   double* __restrict__ out_stock;    // optional: fish_population after growth
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
+  double* __restrict__ out_obs2;     // optional second copy of the observations (zero-copy host front end: out_obs is
+                                     // the device state, out_obs2 a device-mapped pinned host array)
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
   PhiloxKeys keys;                   // round keys of `seed`

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
   const EnvResult e0 = advance<GROWTH, PM, ACT>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
   const EnvResult e1 = advance<GROWTH, PM, ACT>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
   reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
+  if (a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
   st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
   st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
   reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
     const EnvResult e = advance<GROWTH, PM, ACT>(a, i, a.state_in[i], reinterpret_cast<const AT*>(a.action)[i], z, noisy,
                                                  a.years[i], K, r, GROWTH == G_MODEL ? a.model[i] : 0);
     a.out_obs[i] = e.obs;
+    if (a.out_obs2) a.out_obs2[i] = e.obs;
     a.out_reward[i] = e.reward;
     a.out_done[i] = e.done;
     a.years[i] = e.years;

@@ -233,3 +233,34 @@ def test_fused_simulate_matches_the_reference_simulate_tables():
     df = simulate_mdp_fused("fishing-v1", "msy", 1001, sigma=0.05, Tmax=30)
     assert df.rep.max() == 1000 and (df[df.time == 0].action == 0).all() and (df[df.time == 0].reward == 0).all()
     assert df.groupby("rep").time.max().max() == 29
+
+
+def test_step_many_zero_copy_path_with_pinned_host_arrays(monkeypatch):
+    """With FISHING_VEC_ZEROCOPY=1 and page-locked host arrays the kernels read / write host memory directly.  The
+    switch is read once per process, so this test runs in a subprocess-free way only when the variable is already set;
+    otherwise it checks the default staged path on the same pinned arrays."""
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.vec_env import _PinnedArray
+
+    n, T = 6000, 9
+    rng = np.random.default_rng(8)
+    pa, po, pr_, pd = (_PinnedArray(T * n, np.float64), _PinnedArray(T * n, np.float64), _PinnedArray(T * n, np.float64),
+                       _PinnedArray(T * n, np.uint8))
+    acts = pa.array.reshape(T, n)
+    acts[:] = rng.uniform(-1, -0.4, size=(T, n))
+    outs = (po.array.reshape(T, n), pr_.array.reshape(T, n), pd.array.reshape(T, n))
+    for env_id, kw in (("fishing-v1", dict(sigma=0.1, Tmax=5)), ("fishing-v4", dict(sigma=0.05, Tmax=4)),
+                       ("fishing-v10", dict(sigma=0.05, Tmax=6))):
+        a = gf.FishingVecEnv(env_id, num_envs=n, io="numpy", seed=9, **kw)
+        b = gf.FishingVecEnv(env_id, num_envs=n, io="numpy", seed=9, **kw)
+        a.reset(), b.reset()
+        obs, rew, done = a.step_many(acts, out=outs)                       # pinned in and out: zero-copy
+        obs2, rew2, done2 = b.step_many(np.array(acts))                    # pageable: staged copies
+        assert np.array_equal(obs, obs2) and np.array_equal(rew, rew2) and np.array_equal(done, done2)
+        assert done.sum() > n
+        o1, r1, d1, _ = a.step(acts[0])                                    # the handle keeps stepping consistently
+        o2, r2, d2, _ = b.step(acts[0])
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2)
+        a.close(), b.close()
+    for p in (pa, po, pr_, pd):
+        p.free()
