@@ -109,6 +109,24 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 #define FD_SUB(a, b) __dsub_rn((a), (b))
 #define FD_FMA(a, b, c) __fma_rn((a), (b), (c))
 
+// Polynomial coefficients live in constant memory: literal doubles are materialised with two UMOV instructions each,
+// every loop iteration (44 of the 272 instructions of a K2 pair-step); from the constant bank the compiler loads two
+// doubles per LDCU.128 and keeps them in uniform registers across iterations.
+static __constant__ double FD_C[24] = {
+    // [0..6] fdlibm log: Lg7 .. Lg1
+    1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01, 2.222219843214978396e-01,
+    2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01,
+    // [7] ln2_hi, [8] ln2_lo
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,
+    // [9..14] fdlibm kernel sin: S6 .. S1
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    // [15..20] fdlibm kernel cos: C6 .. C1
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    // [21] pi_hi, [22] pi_lo, [23] 2^52 + 2^31
+    3.141592653589793116, 1.2246467991473532e-16, 4503601774854144.0};
+
 // ln(u) for a NORMAL double 0 < u < 1 (fdlibm e_log.c algorithm: u = 2^e * m, m in [sqrt(1/2), sqrt(2)),
 // s = (m-1)/(m+1), log(m) = f - s*(f - R(s^2)), f = m - 1).
 __device__ __forceinline__ double log_unit(double u) {
@@ -130,18 +148,18 @@ __device__ __forceinline__ double log_unit(double u) {
   double s = FD_MUL(f, rg);
   s = FD_FMA(FD_FMA(-s, g, f), rg, s);          // one correction step: s = f/g to < 1 ulp
   const double z = FD_MUL(s, s);
-  double R = 1.479819860511658591e-01;
-  R = FD_FMA(R, z, 1.531383769920937332e-01);
-  R = FD_FMA(R, z, 1.818357216161805012e-01);
-  R = FD_FMA(R, z, 2.222219843214978396e-01);
-  R = FD_FMA(R, z, 2.857142874366239149e-01);
-  R = FD_FMA(R, z, 3.999999999940941908e-01);
-  R = FD_FMA(R, z, 6.666666666666735130e-01);
+  double R = FD_C[0];
+  R = FD_FMA(R, z, FD_C[1]);
+  R = FD_FMA(R, z, FD_C[2]);
+  R = FD_FMA(R, z, FD_C[3]);
+  R = FD_FMA(R, z, FD_C[4]);
+  R = FD_FMA(R, z, FD_C[5]);
+  R = FD_FMA(R, z, FD_C[6]);
   R = FD_MUL(R, z);
   const double lm = FD_FMA(-s, FD_SUB(f, R), f);  // log(m)
   // e as a double without a conversion instruction: the double with bits 0x43300000:(e xor 2^31) is 2^52 + 2^31 + e
-  const double ed = FD_SUB(__hiloint2double(0x43300000, e ^ 0x80000000), 4503601774854144.0);
-  return FD_FMA(ed, 6.93147180369123816490e-01, FD_FMA(ed, 1.90821492927058770002e-10, lm));
+  const double ed = FD_SUB(__hiloint2double(0x43300000, e ^ 0x80000000), FD_C[23]);
+  return FD_FMA(ed, FD_C[7], FD_FMA(ed, FD_C[8], lm));
 }
 
 // sqrt(a) for a normal double a > 0 (no range checks): Newton on the hardware reciprocal-sqrt seed.
@@ -160,21 +178,21 @@ __device__ __forceinline__ void sincospi_02(double t, double& sn, double& cs) {
   const double qd = rint(FD_ADD(t, t));         // nearest quarter-turn index 0..4
   const int q = (int)qd;
   const double y = FD_FMA(qd, -0.5, t);         // exact, |y| <= 1/4
-  const double r = FD_FMA(y, 1.2246467991473532e-16, FD_MUL(y, 3.141592653589793116));  // pi*y, pi = hi + lo
+  const double r = FD_FMA(y, FD_C[22], FD_MUL(y, FD_C[21]));  // pi*y, pi = hi + lo
   const double z = FD_MUL(r, r);
-  double ps = 1.58969099521155010221e-10;
-  ps = FD_FMA(ps, z, -2.50507602534068634195e-08);
-  ps = FD_FMA(ps, z, 2.75573137070700676789e-06);
-  ps = FD_FMA(ps, z, -1.98412698298579493134e-04);
-  ps = FD_FMA(ps, z, 8.33333333332248946124e-03);
-  ps = FD_FMA(ps, z, -1.66666666666666324348e-01);
+  double ps = FD_C[9];
+  ps = FD_FMA(ps, z, FD_C[10]);
+  ps = FD_FMA(ps, z, FD_C[11]);
+  ps = FD_FMA(ps, z, FD_C[12]);
+  ps = FD_FMA(ps, z, FD_C[13]);
+  ps = FD_FMA(ps, z, FD_C[14]);
   const double s = FD_FMA(FD_MUL(r, z), ps, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = FD_FMA(pc, z, 2.08757232129817482790e-09);
-  pc = FD_FMA(pc, z, -2.75573143513906633035e-07);
-  pc = FD_FMA(pc, z, 2.48015872894767294178e-05);
-  pc = FD_FMA(pc, z, -1.38888888888741095749e-03);
-  pc = FD_FMA(pc, z, 4.16666666666666019037e-02);
+  double pc = FD_C[15];
+  pc = FD_FMA(pc, z, FD_C[16]);
+  pc = FD_FMA(pc, z, FD_C[17]);
+  pc = FD_FMA(pc, z, FD_C[18]);
+  pc = FD_FMA(pc, z, FD_C[19]);
+  pc = FD_FMA(pc, z, FD_C[20]);
   const double c = FD_FMA(z, FD_FMA(z, pc, -0.5), 1.0);
   // t = q/2 + y:  q odd -> (sin, cos) = (+-cos, -+sin) of pi*y
   const bool swap = q & 1;
