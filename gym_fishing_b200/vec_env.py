@@ -111,8 +111,8 @@ class LazyInfos:
     """Sequence of per-env info dicts materialised on access (a list of 2^20 dicts per step would dominate the run
     time).  infos[i] == {"terminal_observation": array([s])} if env i finished in this step, else {}."""
 
-    def __init__(self, done, terminal):
-        self._done, self._terminal = done, terminal
+    def __init__(self, done, terminal, episode=None):
+        self._done, self._terminal, self._episode = done, terminal, episode
 
     def __len__(self):
         return len(self._done)
@@ -120,11 +120,16 @@ class LazyInfos:
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
-        if bool(self._done[i]) and self._terminal is not None:
+        if not bool(self._done[i]):
+            return {}
+        info = {}
+        if self._terminal is not None:
             t = self._terminal[i]
-            t = t.reshape(1) if hasattr(t, "reshape") else np.array([t])
-            return {"terminal_observation": t}
-        return {}
+            info["terminal_observation"] = t.reshape(1) if hasattr(t, "reshape") else np.array([t])
+        if self._episode is not None:      # VecMonitor-style statistics of the episode that just ended
+            r, l = self._episode
+            info["episode"] = {"r": float(r[i]), "l": int(l[i])}
+        return info
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -167,7 +172,9 @@ class _PinnedArray:
 
 class FishingVecEnv:
     def __init__(self, env_id="fishing-v1", num_envs=1, *, device="cuda", io="torch", seed=0, auto_reset=True,
-                 env_id_offset=0, **env_kwargs):
+                 env_id_offset=0, monitor=False, **env_kwargs):
+        """monitor=True (torch mode): keep per-env episode return / length on the device and report them in
+        infos[i]["episode"] = {"r", "l"} when an episode ends, like stable-baselines3's VecMonitor."""
         if env_id not in nat.KIND_OF_ID:
             raise KeyError(f"unknown environment id {env_id!r}")
         if io not in ("torch", "numpy"):
@@ -187,6 +194,9 @@ class FishingVecEnv:
         self.action_space = Discrete(self.cfg["n_actions"]) if self.kind == nat.V0 else unit_box()
         self.metadata = {"render.modes": ["human"]}
         self._pending = None
+        self.monitor = bool(monitor)
+        if self.monitor and io != "torch":
+            raise ValueError("monitor=True needs io='torch'")
         self._steps_done = 0
         self._closed = False
         self._handle = None
@@ -202,6 +212,11 @@ class FishingVecEnv:
             self._reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
             self._done = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
             self.terminal_obs = torch.full((self.num_envs,), float("nan"), dtype=torch.float64, device=self.device)
+            if self.monitor:
+                self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+                self.ep_length = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+                self.last_ep_return = torch.zeros_like(self.ep_return)
+                self.last_ep_length = torch.zeros_like(self.ep_length)
         else:
             import torch
 
@@ -236,6 +251,9 @@ class FishingVecEnv:
         self._check_open()
         if self.io == "torch":
             s = self.batch.reset()
+            if self.monitor:
+                self.ep_return.zero_()
+                self.ep_length.zero_()
             return s.view(self.num_envs, 1)
         nat.check(nat.lib().fishing_vec_reset(self._handle, self._h_obs.array.ctypes.data), "fishing_vec_reset")
         return self._h_obs.array.reshape(self.num_envs, 1)
@@ -279,7 +297,17 @@ class FishingVecEnv:
         a = self._coerce_torch_actions(actions)
         obs, rew, done = b.step(a, out_reward=self._reward, out_done=self._done,
                                 out_terminal=self.terminal_obs if self.auto_reset else None)
-        return obs.view(self.num_envs, 1), rew, done.view(b.torch.bool), LazyInfos(done, self.terminal_obs)
+        done_b = done.view(b.torch.bool)
+        episode = None
+        if self.monitor:
+            self.ep_return += rew
+            self.ep_length += 1
+            b.torch.where(done_b, self.ep_return, self.last_ep_return, out=self.last_ep_return)
+            b.torch.where(done_b, self.ep_length, self.last_ep_length, out=self.last_ep_length)
+            self.ep_return.masked_fill_(done_b, 0.0)
+            self.ep_length.masked_fill_(done_b, 0)
+            episode = (self.last_ep_return, self.last_ep_length)
+        return obs.view(self.num_envs, 1), rew, done_b, LazyInfos(done, self.terminal_obs, episode)
 
     def step_into(self, actions, out_obs, out_reward, out_done, out_terminal=None, noise=None):
         """torch mode, rollout-buffer form: write this step's observations / rewards / dones straight into the given

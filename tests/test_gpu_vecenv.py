@@ -264,3 +264,28 @@ def test_step_many_zero_copy_path_with_pinned_host_arrays(monkeypatch):
         a.close(), b.close()
     for p in (pa, po, pr_, pd):
         p.free()
+
+
+def test_monitor_episode_statistics():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 256, 40
+    venv = gf.FishingVecEnv("fishing-v1", num_envs=n, sigma=0.0, Tmax=7, monitor=True)
+    venv.reset()
+    rng = np.random.default_rng(0)
+    ret, length = np.zeros(n), np.zeros(n, dtype=int)
+    seen = 0
+    for t in range(T):
+        a = rng.uniform(-1, -0.7, size=(n, 1))
+        obs, rew, done, infos = venv.step(torch.as_tensor(a, device="cuda"))
+        ret += rew.cpu().numpy()
+        length += 1
+        for i in np.flatnonzero(done.cpu().numpy())[:5]:
+            ep = infos[int(i)]["episode"]
+            assert ep["l"] == length[i] and abs(ep["r"] - ret[i]) < 1e-12
+            seen += 1
+        d = done.cpu().numpy()
+        ret[d], length[d] = 0.0, 0
+    assert seen > 10
