@@ -256,7 +256,7 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
 int fishing_step_many(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step0, int64_t T,
                       const void* actions, int32_t action_dtype, const double* noise, fishing_soa soa, double* out_obs,
                       double* out_reward, uint8_t* out_done, double* out_terminal, void* stream) {
-  if (T < 0 || n < 0) return FISHING_E_ARG;
+  if (!p || !actions || !out_obs || !out_reward || !out_done || T < 0 || n < 0) return FISHING_E_ARG;
   const int asz = act_size(action_dtype);
   if (!asz) return FISHING_E_ARG;
   // consecutive steps may overlap (PDL) when no step's inputs alias any step's outputs

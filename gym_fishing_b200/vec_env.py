@@ -209,8 +209,11 @@ class FishingVecEnv:
                                   **growth_kwargs(self.kind, env_kwargs))
             self.device = self.batch.device
             torch = self.batch.torch
-            self._reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
-            self._done = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+            # two sets of output buffers used alternately: what step() returns stays valid until the next-but-one call
+            self._obs2 = [self.batch.state, torch.empty_like(self.batch.state)]
+            self._reward2 = [torch.empty(self.num_envs, dtype=torch.float64, device=self.device) for _ in range(2)]
+            self._done2 = [torch.empty(self.num_envs, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._flip = 0
             self.terminal_obs = torch.full((self.num_envs,), float("nan"), dtype=torch.float64, device=self.device)
             if self.monitor:
                 self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
@@ -239,9 +242,9 @@ class FishingVecEnv:
                                                ct.byref(h)), "fishing_vec_create")
         self._handle = h
         n = self.num_envs
-        self._h_obs = _PinnedArray(n, np.float64)
-        self._h_reward = _PinnedArray(n, np.float64)
-        self._h_done = _PinnedArray(n, np.uint8)
+        self._h_sets = [(_PinnedArray(n, np.float64), _PinnedArray(n, np.float64), _PinnedArray(n, np.uint8)) for _ in range(2)]
+        self._h_flip = 0
+        self._h_obs, self._h_reward, self._h_done = self._h_sets[0]
         self._h_term = _PinnedArray(n, np.float64)
         self._h_act = _PinnedArray(n, np.float64)  # staging for pageable / wrongly-typed actions (8 bytes per env)
 
@@ -250,6 +253,7 @@ class FishingVecEnv:
         """-> observations [num_envs, 1] float64 (BaseFishingEnv.reset, base_fishing_env.py:83-91; v4 redraws K, r)."""
         self._check_open()
         if self.io == "torch":
+            self.batch.state = self._obs2[self._flip]
             s = self.batch.reset()
             if self.monitor:
                 self.ep_return.zero_()
@@ -295,7 +299,9 @@ class FishingVecEnv:
     def _step_torch(self, actions):
         b = self.batch
         a = self._coerce_torch_actions(actions)
-        obs, rew, done = b.step(a, out_reward=self._reward, out_done=self._done,
+        self._flip ^= 1
+        k = self._flip
+        obs, rew, done = b.step(a, out_obs=self._obs2[k], out_reward=self._reward2[k], out_done=self._done2[k],
                                 out_terminal=self.terminal_obs if self.auto_reset else None)
         done_b = done.view(b.torch.bool)
         episode = None
@@ -334,6 +340,8 @@ class FishingVecEnv:
                 a = a.astype(np.float64, copy=False)
                 adt = nat.ACT_F64
         a = np.ascontiguousarray(a.reshape(n))
+        self._h_flip ^= 1
+        self._h_obs, self._h_reward, self._h_done = self._h_sets[self._h_flip]
         rc = nat.lib().fishing_vec_step(self._handle, a.ctypes.data, adt, None, self._h_obs.array.ctypes.data,
                                         self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data, None)
         nat.check(rc, "fishing_vec_step")
@@ -468,7 +476,7 @@ class FishingVecEnv:
         if self._handle is not None:
             nat.lib().fishing_vec_destroy(self._handle)
             self._handle = None
-            for a in (self._h_obs, self._h_reward, self._h_done, self._h_term, self._h_act):
+            for a in (*self._h_sets[0], *self._h_sets[1], self._h_term, self._h_act):
                 a.free()
 
     def __del__(self):  # pragma: no cover
