@@ -616,3 +616,56 @@ def test_fast_rollout_kernel_equals_generic_kernel_with_philox(kind, cfg, mode, 
             if x is not None:
                 assert torch.equal(x, y), (kind, mode, policy)
         assert (res[0][1] >= 0).any()
+
+
+def test_special_values_bitwise_against_oracle():
+    """NaN / inf / negative / signed-zero states, actions and noise through K1 (both paths) and K2: the comparisons
+    removed from the kernels as provably redundant (max(x - h, 0), ...) must not change any bit on any input."""
+    torch = _torch()
+    from gym_fishing_b200.engine import EnvBatch
+
+    specials = np.array([np.nan, np.inf, -np.inf, -5.0, -1.0, -1.0 + 2 ** -52, -0.0, 0.0, 2 ** -1074, 1e-310, 0.25, 1.0, 7.0,
+                         1e300, -1e300])
+    acts = np.array([np.nan, np.inf, -np.inf, -2.0, -1.0, -0.999, -0.0, 0.0, 0.5, 1.0, 1.5])
+    zs = np.array([0.0, -0.0, 1.0, -3.0, 40.0, np.nan, np.inf])
+    S, A, Z = np.meshgrid(specials, acts, zs, indexing="ij")
+    s0, a0, z0 = S.ravel(), A.ravel(), Z.ravel()
+    if s0.size % 2:
+        s0, a0, z0 = s0[:-1], a0[:-1], z0[:-1]
+    n = s0.size
+    for kind, code, cfg in (("v1", 1, dict(r=0.3, K=1.0, sigma=0.2)), ("v1", 1, dict(r=0.7, K=2.5, sigma=0.2)),
+                            ("v2", 2, dict(r=0.3, K=1.0, sigma=0.2, C=0.5)), ("v4", 4, dict(r=0.3, K=1.0, sigma=0.2))):
+        for sub in (slice(0, n), slice(1, n)):          # even (vector path) and odd offset (scalar path)
+            m = s0[sub].size
+            b = EnvBatch(code, m, Tmax=3, x0=0.75, **cfg)
+            b.reset()
+            b.state.copy_(dev(s0[sub]))
+            K = b.K_env.cpu().numpy() if kind == "v4" else cfg["K"]
+            r = b.r_env.cpu().numpy() if kind == "v4" else cfg["r"]
+            with np.errstate(all="ignore"):
+                e_s, e_r, e_d, _ = fo.step_vec(kind, s0[sub], a0[sub], z0[sub], np.zeros(m, dtype=np.int64), r=r, K=K,
+                                               sigma=0.2, C=cfg.get("C", 0.5), Tmax=3)
+            o, rw, d = b.step(dev(a0[sub]), noise=dev(z0[sub]))
+            o, rw, d = o.cpu().numpy(), rw.cpu().numpy(), d.cpu().numpy()
+            assert np.array_equal(d.astype(bool), e_d), (kind, cfg)
+            if kind == "v2":
+                ok = np.isclose(o, e_s, rtol=1e-12, atol=1e-12, equal_nan=True) | (np.isinf(o) & (o == e_s))
+                assert ok.all() and np.array_equal(rw, e_r, equal_nan=True)
+            else:
+                assert np.array_equal(o, e_s, equal_nan=True) and np.array_equal(rw, e_r, equal_nan=True), (kind, cfg)
+                assert np.array_equal(np.signbit(o[~np.isnan(o)]), np.signbit(e_s[~np.isnan(e_s)]))
+    # fused kernels (generic with trace, fast without) on the same special states, escapement policy, sigma = 0
+    for K in (1.0, 2.5):
+        outs = []
+        for traced in (True, False):
+            b = EnvBatch(1, n, r=0.3, K=K, sigma=0.0, Tmax=100, x0=0.75)
+            b.reset()
+            b.state.copy_(dev(s0))
+            out = b.rollout(6, policy="escapement", S=0.4 * K, trace=traced)
+            outs.append((out["ret"].cpu().numpy(), out["done_step"].cpu().numpy(), b.state.cpu().numpy()))
+        with np.errstate(all="ignore"):
+            e = fo.rollout_vec("v1", 6, n, r=0.3, K=K, sigma=0.0, x0=0.75, Tmax=100, policy="escapement", S=0.4 * K, s0=s0,
+                               record=False)
+        for ret, ds, st in outs:
+            assert np.array_equal(ret, e["ret"], equal_nan=True) and np.array_equal(ds, e["done_step"])
+            assert np.array_equal(st, e["final_state"], equal_nan=True)
