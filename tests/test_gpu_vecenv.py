@@ -289,3 +289,58 @@ def test_monitor_episode_statistics():
         d = done.cpu().numpy()
         ret[d], length[d] = 0.0, 0
     assert seen > 10
+
+
+def test_render_file_logging_and_abi_error_codes(tmp_path):
+    """f4: render() writes the reference's CSV row [years_passed, state, action, reward] (shared_env.py:8-12; upstream
+    raises AttributeError there because `self.action` is never assigned).  Plus the argument errors of the C ABI."""
+    import ctypes as ct
+
+    import torch
+
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200 import _native as nat
+
+    path = tmp_path / "log.csv"
+    env = gf.make("fishing-v1", sigma=0.0, file=str(path))
+    env.reset()
+    for a in (-0.9, -0.8):
+        env.step(np.array([a]))
+        row = env.render()
+        assert row[0] == env.years_passed and row[1] == env.state[0] and row[3] == env.reward
+    env.close()
+    lines = path.read_text().strip().splitlines()
+    assert len(lines) == 2 and lines[0].startswith("1,")
+
+    lib = nat.lib()
+    p = nat.make_params(nat.V1)
+    n = 64
+    st = torch.zeros(n, dtype=torch.float64, device="cuda")
+    yr = torch.zeros(n, dtype=torch.int32, device="cuda")
+    act = torch.zeros(n, dtype=torch.float64, device="cuda")
+    rew = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dn = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    soa = nat.FishingSoA(st.data_ptr(), yr.data_ptr(), None, None, None)
+    args = lambda **kw: (ct.byref(kw.get("p", p)), kw.get("n", n), 0, 0, kw.get("act", act.data_ptr()), kw.get("dt", nat.ACT_F64),  # noqa: E731
+                         None, None, kw.get("soa", soa), st.data_ptr(), rew.data_ptr(), dn.data_ptr(), None, None, None, None)
+    assert lib.fishing_step(*args()) == 0
+    assert lib.fishing_step(*args(n=-1)) == -1                      # FISHING_E_ARG
+    assert lib.fishing_step(*args(act=None)) == -1
+    assert lib.fishing_step(*args(dt=nat.ACT_I64)) == -2            # FISHING_E_KIND: integer action on a Box env
+    assert lib.fishing_step(*args(dt=7)) == -1
+    assert lib.fishing_step(*args(act=act.data_ptr() + 4)) == -3    # FISHING_E_ALIGN
+    bad = nat.make_params(3)
+    assert lib.fishing_step(*args(p=bad)) == -1                     # there is no fishing-v3
+    v4 = nat.make_params(nat.V4)
+    assert lib.fishing_step(*args(p=v4)) == -1                      # v4 needs K_env / r_env
+    assert lib.fishing_step(*args(n=0)) == 0
+    assert b"not valid" in lib.fishing_error_string(-2) and lib.fishing_error_string(700) is not None
+    torch.cuda.synchronize()
+    h = ct.c_void_p()
+    assert lib.fishing_vec_create(ct.byref(p), 16, 0, 99, ct.byref(h)) == -4       # FISHING_E_NODEVICE
+    assert lib.fishing_vec_create(ct.byref(p), 16, 0, 0, ct.byref(h)) == 0
+    buf = np.zeros(16)
+    d8 = np.zeros(16, dtype=np.uint8)
+    assert lib.fishing_vec_step(h, buf.ctypes.data, nat.ACT_F64, None, buf.ctypes.data, buf.ctypes.data, d8.ctypes.data, None) == -5
+    assert lib.fishing_vec_reset(h, buf.ctypes.data) == 0 and buf[0] == -0.25
+    assert lib.fishing_vec_destroy(h) == 0
