@@ -1,21 +1,14 @@
-"""Environment classes and id registration (mirrors gym_fishing/envs/__init__.py:17-35 for the four ids in scope)."""
+"""Environment classes and id registration (the ids of gym_fishing/envs/__init__.py:17-71; the reference has no
+fishing-v3).  v0/v1/v2/v4 are the hot-path rows of SURVEY.md section 8a, v5..v11 the "next" row f1."""
 from ..registration import register
 from .base import BaseFishingEnv, FishingCtsEnv, FishingEnv, FishingModelError, FishingTippingEnv
+from .growth_models import Allen, BevertonHolt, May, ModelUncertainty, Myers, NonStationary, Ricker
 
-register(id="fishing-v0", entry_point="gym_fishing_b200.envs:FishingEnv")
-register(id="fishing-v1", entry_point="gym_fishing_b200.envs:FishingCtsEnv")
-register(id="fishing-v2", entry_point="gym_fishing_b200.envs:FishingTippingEnv")
-register(id="fishing-v4", entry_point="gym_fishing_b200.envs:FishingModelError")
+ENV_CLASSES = {
+    0: FishingEnv, 1: FishingCtsEnv, 2: FishingTippingEnv, 4: FishingModelError,
+    5: Allen, 6: BevertonHolt, 7: May, 8: Myers, 9: Ricker, 10: NonStationary, 11: ModelUncertainty,
+}
+for _version, _cls in ENV_CLASSES.items():
+    register(f"fishing-v{_version}", f"{__name__}:{_cls.__name__}")
 
-from .growth_models import Allen, BevertonHolt, May, ModelUncertainty, Myers, NonStationary, Ricker  # noqa: E402
-
-# "next row" f1: gym_fishing/envs/__init__.py:38-71
-register(id="fishing-v5", entry_point="gym_fishing_b200.envs:Allen")
-register(id="fishing-v6", entry_point="gym_fishing_b200.envs:BevertonHolt")
-register(id="fishing-v7", entry_point="gym_fishing_b200.envs:May")
-register(id="fishing-v8", entry_point="gym_fishing_b200.envs:Myers")
-register(id="fishing-v9", entry_point="gym_fishing_b200.envs:Ricker")
-register(id="fishing-v10", entry_point="gym_fishing_b200.envs:NonStationary")
-register(id="fishing-v11", entry_point="gym_fishing_b200.envs:ModelUncertainty")
-
-__all__ = ["Allen", "BevertonHolt", "May", "Myers", "Ricker", "NonStationary", "ModelUncertainty", "BaseFishingEnv", "FishingEnv", "FishingCtsEnv", "FishingTippingEnv", "FishingModelError"]
+__all__ = ["BaseFishingEnv", "ENV_CLASSES"] + [c.__name__ for c in ENV_CLASSES.values()]
