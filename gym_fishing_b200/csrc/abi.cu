@@ -38,10 +38,22 @@ static bool kind_ok(int kind) {
 }
 static bool is_lognormal(int kind) { return kind >= FISHING_V5 && kind <= FISHING_V11; }
 
+static int growth_fn_of_kind(int kind) {
+  switch (kind) {
+    case FISHING_V5: return FISHING_FN_ALLEN;
+    case FISHING_V6: case FISHING_V10: return FISHING_FN_BEVERTON_HOLT;
+    case FISHING_V7: return FISHING_FN_MAY;
+    case FISHING_V8: return FISHING_FN_MYERS;
+    case FISHING_V9: return FISHING_FN_RICKER;
+    default: return -1;
+  }
+}
+
 static GrowthP growth_of(const fishing_params* p) {
   GrowthP g;
   g.r = p->r; g.K = p->growth_K; g.C = p->C; g.M = p->M; g.theta = p->theta; g.q = p->q; g.b = p->b; g.a = p->a;
   g.sigma = p->sigma;
+  growth_derive(g, growth_fn_of_kind(p->kind));
   return g;
 }
 
@@ -57,6 +69,7 @@ static int fill_table(const fishing_params* p, ModelTable* t, double* any_sigma)
     const fishing_growth_params& m = p->model_params[i];
     t->p[i].r = m.r; t->p[i].K = m.K; t->p[i].C = m.C; t->p[i].M = m.M; t->p[i].theta = m.theta; t->p[i].q = m.q;
     t->p[i].b = m.b; t->p[i].a = m.a; t->p[i].sigma = m.sigma;
+    growth_derive(t->p[i], t->fn[i]);
     if (m.sigma != 0.0) *any_sigma = 1.0;
   }
   return 0;
@@ -241,6 +254,7 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
     volatile double r_next = p->r + p->alpha;
     a.gp.r = r_next;
   }
+  a.derive_on_device = p->kind == FISHING_V10;   // so that K1 and the fused K2 (which drifts r in-kernel) agree bit for bit
   // 16-byte vector path: every array that is accessed two-wide must be aligned to its pair size
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
@@ -400,6 +414,7 @@ int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int
   if (p->kind == FISHING_V10) {
     volatile double r_next = p->r + p->alpha;
     g.r = r_next;
+    growth_derive(g, fn);
   }
   return (int)launch_growth_ln(fn, n, x, g, z, out, static_cast<cudaStream_t>(stream));
 }

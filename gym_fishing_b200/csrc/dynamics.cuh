@@ -15,7 +15,27 @@ enum Growth { LOGISTIC = 0, TIPPING = 1,
 // growth-function parameters of the log-normal family (the reference's `params` dict) and the fishing-v11 model table
 struct GrowthP {
   double r, K, C, M, theta, q, b, a, sigma;
+  // loop-invariant sub-expressions of mu(x), derived once per launch on the host (or per step on the device for the
+  // drifting r of fishing-v10) instead of once per environment-step:
+  double logA;  // Beverton-Holt: log(clip(r,0,inf) + 1); Myers: log(r + 1)
+  double B;     // Beverton-Holt: clip(K,0,inf) / clip(r,0,inf)
+  double omC;   // Allen: 1 - C
+  double bq;    // May: b^q
 };
+
+// the derived fields, same operations as the reference's expressions (growth_models.py:213-215,222-225,239,248-253)
+__host__ __device__ inline void growth_derive(GrowthP& g, int fn) {
+  g.logA = 0.0; g.B = 0.0; g.omC = 1.0 - g.C; g.bq = 0.0;
+  if (fn == FISHING_FN_BEVERTON_HOLT) {
+    const double rc = (g.r < 0.0) ? 0.0 : g.r;
+    g.logA = log(rc + 1.0);
+    g.B = ((g.K < 0.0) ? 0.0 : g.K) / rc;
+  } else if (fn == FISHING_FN_MYERS) {
+    g.logA = log(g.r + 1.0);
+  } else if (fn == FISHING_FN_MAY) {
+    g.bq = pow(g.b, g.q);
+  }
+}
 struct ModelTable {
   int32_t n_models;
   int32_t fn[FISHING_MAX_MODELS];
@@ -89,22 +109,18 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
 template <int FN>
 __device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
   if (FN == FISHING_FN_ALLEN) {            // np.log(x) + r * (1 - x / K) * (1 - C) / K
-    const double y = __ddiv_rn(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))), __dsub_rn(1.0, g.C)), g.K);
+    const double y = __ddiv_rn(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))), g.omC), g.K);
     return __dadd_rn(log(x), y);
-  } else if (FN == FISHING_FN_BEVERTON_HOLT) {
+  } else if (FN == FISHING_FN_BEVERTON_HOLT) {   // log(A) + log(x) - log(1 + x / B), A = r + 1, B = K / r
     const double xc = (x < 0.0) ? 0.0 : x;                       // np.clip(x, 0, inf)
-    const double rc = (g.r < 0.0) ? 0.0 : g.r;
-    const double A = __dadd_rn(rc, 1.0);
-    const double B = __ddiv_rn((g.K < 0.0) ? 0.0 : g.K, rc);
-    return __dsub_rn(__dadd_rn(log(A), log(xc)), log(__dadd_rn(1.0, __ddiv_rn(xc, B))));
+    return __dsub_rn(__dadd_rn(g.logA, log(xc)), log(__dadd_rn(1.0, __ddiv_rn(xc, g.B))));
   } else if (FN == FISHING_FN_MAY) {       // x + x*r*(1 - x/M) - a*x^q / (x^q + b^q), then log
     const double xq = pow(x, g.q);
     const double e = __dsub_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(x, g.r), __dsub_rn(1.0, __ddiv_rn(x, g.M)))),
-                               __ddiv_rn(__dmul_rn(g.a, xq), __dadd_rn(xq, pow(g.b, g.q))));
+                               __ddiv_rn(__dmul_rn(g.a, xq), __dadd_rn(xq, g.bq)));
     return log(e);
   } else if (FN == FISHING_FN_MYERS) {     // log(r + 1) + theta*log(x) - log(1 + x^theta / M)
-    const double A = __dadd_rn(g.r, 1.0);
-    return __dsub_rn(__dadd_rn(log(A), __dmul_rn(g.theta, log(x))),
+    return __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, log(x))),
                      log(__dadd_rn(1.0, __ddiv_rn(pow(x, g.theta), g.M))));
   } else {                                 // Ricker: log(x) + r * (1 - x / K)
     return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))));

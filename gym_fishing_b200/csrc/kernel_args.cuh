@@ -40,6 +40,7 @@ struct StepArgs {
                                      // the device state, out_obs2 a device-mapped pinned host array)
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
+  int32_t derive_on_device;          // fishing-v10: recompute gp's derived fields with the device's log (like K2 does)
   PhiloxKeys keys;                   // round keys of `seed`
   int32_t* model;                    // v11: per-env model index (updated at auto-reset)
   ModelTable tab;                    // v11: the model table (by value in the kernel parameters)

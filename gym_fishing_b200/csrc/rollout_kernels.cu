@@ -247,7 +247,10 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 
   for (int64_t t = 0; t < a.T; ++t) {
     if (e0.frozen && e1.frozen && !tracing) break;
-    if (a.nonstationary) gp.r = __dadd_rn(gp.r, a.alpha);
+    if (a.nonstationary) {
+      gp.r = __dadd_rn(gp.r, a.alpha);
+      growth_derive(gp, FISHING_FN_BEVERTON_HOLT);
+    }
     double z0 = 0.0, z1 = 0.0;
     if (ext_noise) {
       const double2 z = load2_stream<double2>(a.noise + t * a.n, L);

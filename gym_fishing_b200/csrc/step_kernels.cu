@@ -24,7 +24,14 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
                                              double z, bool noisy, int32_t years, double K, double r,
                                              int32_t model = 0) {
   const double quota = quota_of<PM, ACT>(act, a.n_actions, K);
-  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy, &a.gp, &a.tab, model);
+  GrowthP gp_local;
+  const GrowthP* gp = &a.gp;
+  if (GROWTH == G_BEVERTON_HOLT && a.derive_on_device) {
+    gp_local = a.gp;
+    growth_derive(gp_local, FISHING_FN_BEVERTON_HOLT);
+    gp = &gp_local;
+  }
+  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy, gp, &a.tab, model);
   EnvResult e;
   e.model = model;
   e.years = years + 1;                                   // base_fishing_env.py:75
