@@ -96,10 +96,18 @@ def main():
 
         ms_env, _ = timed(env_only, dev)
         ms_c, _ = timed(env_only_c_loop, dev)
+        # the same with a policy-like action distribution (small quotas: episodes mostly end at the time limit, ~1 % of the
+        # environments reset per step instead of ~10 %); the per-warp cost of the divergent v4 reset path drops accordingly
+        fixed_actions.uniform_(-1.0, -0.93)
+        ms_c_gentle, _ = timed(env_only_c_loop, dev)
+        done_rate_gentle = float(done_buf.float().mean())
+        fixed_actions.uniform_(-1.0, -0.6)
         ms_pol, _ = timed(env_and_policy, dev)
         lines.append({"config": "cfg4", "env": "fishing-v4", "n_envs_per_gpu": n, "n_steps": n_steps, "n_gpus": world,
                       "ms_env_only": ms_env, "env_steps_per_s_env_only": world * n * n_steps / (ms_env * 1e-3),
                       "ms_env_only_c_loop": ms_c, "env_steps_per_s_env_only_c_loop": world * n * n_steps / (ms_c * 1e-3),
+                      "ms_env_only_c_loop_gentle_actions": ms_c_gentle, "done_rate_gentle": done_rate_gentle,
+                      "env_steps_per_s_env_only_c_loop_gentle_actions": world * n * n_steps / (ms_c_gentle * 1e-3),
                       "ms_env_plus_policy": ms_pol, "env_steps_per_s_env_plus_policy": world * n * n_steps / (ms_pol * 1e-3),
                       "bytes_per_env_step": 57, "done_rate_last": float(done_buf[-1].float().mean()),
                       "mean_reward_last": float(rew_buf[-1].mean())})

@@ -55,6 +55,19 @@ __device__ __forceinline__ double np_max0(double a) { return (a > 0.0 || a != a)
 __device__ __forceinline__ double np_clip(double a, double lo, double hi) { return (a < lo) ? lo : ((a > hi) ? hi : a); }
 __device__ __forceinline__ float np_clipf(float a, float lo, float hi) { return (a < lo) ? lo : ((a > hi) ? hi : a); }
 
+// IEEE a / b for the quotients of this file, whose numerators are very often exactly zero (an extinct stock, a zero
+// quota, action 0).  The hardware division sequence sends a zero numerator to its ~55-instruction slow path, and one such
+// lane drags its whole warp there; the profile of the fishing-v4 kernel showed 220 of 880 instructions per environment
+// pair in that subroutine.  A zero numerator has a known quotient -- zero with the sign of a*b, or NaN when b is 0 or
+// NaN -- so it is substituted by 1.0 for the division proper and patched afterwards.  Bit-identical to a / b.
+__device__ __forceinline__ double div_z(double a, double b) {
+  const bool z = (a == 0.0);
+  const double q = __ddiv_rn(z ? 1.0 : a, b);
+  if (!z) return q;
+  const double signed_zero = __dmul_rn(a, (b < 0.0) ? -1.0 : 1.0);
+  return (b == b && b != 0.0) ? signed_zero : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // get_quota, base_fishing_env.py:135-147
 template <int PM>
 __device__ __forceinline__ double quota_f64(double a, double K) {
@@ -72,25 +85,25 @@ __device__ __forceinline__ double quota_f32(float a, double K) {
 }
 template <int PM>
 __device__ __forceinline__ double quota_int(long long a, double n_actions, double K) {
-  const double t = __ddiv_rn((double)a, n_actions);
+  const double t = div_z((double)a, n_actions);
   return PM == P_KONE ? t : __dmul_rn(t, K);
 }
 
 // get_action, base_fishing_env.py:149-156
 template <int PM>
 __device__ __forceinline__ double action_cts(double q, double K) {
-  return __dsub_rn(PM == P_KONE ? q : __ddiv_rn(q, K), 1.0);
+  return __dsub_rn(PM == P_KONE ? q : div_z(q, K), 1.0);
 }
 template <int PM>
 __device__ __forceinline__ double action_discrete(double q, double n_actions, double K) {
   const double t = __dmul_rn(q, n_actions);
-  return rint(PM == P_KONE ? t : __ddiv_rn(t, K));  // Python round(): half to even, not range checked
+  return rint(PM == P_KONE ? t : div_z(t, K));  // Python round(): half to even, not range checked
 }
 
 // population_draw: base_fishing_env.py:121-133 (logistic) / fishing_tipping_env.py:24-35 (tipping point)
 template <int GROWTH, int PM>
 __device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy) {
-  const double frac = PM == P_KONE ? x1 : __ddiv_rn(x1, K);
+  const double frac = PM == P_KONE ? x1 : div_z(x1, K);
   const double room = __dsub_rn(1.0, frac);
   if (GROWTH == LOGISTIC) {
     double t = __dadd_rn(x1, __dmul_rn(__dmul_rn(r, x1), room));
@@ -109,21 +122,21 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
 template <int FN>
 __device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
   if (FN == FISHING_FN_ALLEN) {            // np.log(x) + r * (1 - x / K) * (1 - C) / K
-    const double y = __ddiv_rn(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))), g.omC), g.K);
+    const double y = div_z(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_z(x, g.K))), g.omC), g.K);
     return __dadd_rn(log(x), y);
   } else if (FN == FISHING_FN_BEVERTON_HOLT) {   // log(A) + log(x) - log(1 + x / B), A = r + 1, B = K / r
     const double xc = (x < 0.0) ? 0.0 : x;                       // np.clip(x, 0, inf)
-    return __dsub_rn(__dadd_rn(g.logA, log(xc)), log(__dadd_rn(1.0, __ddiv_rn(xc, g.B))));
+    return __dsub_rn(__dadd_rn(g.logA, log(xc)), log(__dadd_rn(1.0, div_z(xc, g.B))));
   } else if (FN == FISHING_FN_MAY) {       // x + x*r*(1 - x/M) - a*x^q / (x^q + b^q), then log
     const double xq = pow(x, g.q);
-    const double e = __dsub_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(x, g.r), __dsub_rn(1.0, __ddiv_rn(x, g.M)))),
-                               __ddiv_rn(__dmul_rn(g.a, xq), __dadd_rn(xq, g.bq)));
+    const double e = __dsub_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(x, g.r), __dsub_rn(1.0, div_z(x, g.M)))),
+                               div_z(__dmul_rn(g.a, xq), __dadd_rn(xq, g.bq)));
     return log(e);
   } else if (FN == FISHING_FN_MYERS) {     // log(r + 1) + theta*log(x) - log(1 + x^theta / M)
     return __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, log(x))),
-                     log(__dadd_rn(1.0, __ddiv_rn(pow(x, g.theta), g.M))));
+                     log(__dadd_rn(1.0, div_z(pow(x, g.theta), g.M))));
   } else {                                 // Ricker: log(x) + r * (1 - x / K)
-    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, __ddiv_rn(x, g.K))));
+    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, div_z(x, g.K))));
   }
 }
 
@@ -182,7 +195,7 @@ __device__ __forceinline__ StepOut step_core(double s, double quota, double z, d
   if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
   else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);
   StepOut o;
-  o.s2 = __dsub_rn(PM == P_KONE ? x2 : __ddiv_rn(x2, K), 1.0);  // get_state :162-164
+  o.s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, K), 1.0);  // get_state :162-164
   o.reward = py_max(h, 0.0);                        // :74
   o.dead = x2 <= 0.0;                               // :78
   o.stock = x2;

@@ -99,7 +99,7 @@ __device__ __forceinline__ double policy_quota_escapement(const RolloutArgs& a, 
   if (a.discrete) {
     const double act = action_discrete<PM>(q, a.n_actions, e.K);
     action_out = act;
-    const double t = __ddiv_rn(act, a.n_actions);
+    const double t = div_z(act, a.n_actions);
     return PM == P_KONE ? t : __dmul_rn(t, e.K);
   }
   const double act = action_cts<PM>(q, e.K);
@@ -113,7 +113,7 @@ __device__ __forceinline__ double policy_quota_msy(const RolloutArgs& a, double 
   if (a.discrete) {
     const double act = action_discrete<PM>(a.msy_q, a.n_actions, K);
     action_out = act;
-    const double t = __ddiv_rn(act, a.n_actions);
+    const double t = div_z(act, a.n_actions);
     return PM == P_KONE ? t : __dmul_rn(t, K);
   }
   const double act = action_cts<PM>(a.msy_q, K);
@@ -330,7 +330,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
   const double h = py_min(x, quota);
   const double x1 = __dsub_rn(x, h);                             // == max(x - h, 0.0)
-  const double frac = PM == P_KONE ? x1 : __ddiv_rn(x1, e.K);
+  const double frac = PM == P_KONE ? x1 : div_z(x1, e.K);
   const double room = __dsub_rn(1.0, frac);
   double g;
   if (GROWTH == LOGISTIC) {
@@ -343,7 +343,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
   const double x2 = alive ? g : 0.0;
-  const double s2 = __dsub_rn(PM == P_KONE ? x2 : __ddiv_rn(x2, e.K), 1.0);
+  const double s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, e.K), 1.0);
   const double reward = py_max(h, 0.0);
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;

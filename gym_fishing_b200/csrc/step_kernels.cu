@@ -19,7 +19,7 @@ struct EnvResult {
   double terminal, stock, harvest;
 };
 
-template <int GROWTH, int PM, int ACT>
+template <int GROWTH, int PM, int ACT, bool DEFER_V4_DRAW = false>
 __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, double s, typename ActT<ACT>::type act,
                                              double z, bool noisy, int32_t years, double K, double r,
                                              int32_t model = 0) {
@@ -47,13 +47,13 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
   if ((a.flags & FISHING_AUTO_RESET) && e.done) {        // SB3 VecEnv: reset inside the step that ended the episode
     e.reset_fired = true;
     e.years = 0;
-    if (PM == P_PERENV) {                                // FishingModelError.reset, fishing_model_error.py:41-48
+    if (PM == P_PERENV && !(DEFER_V4_DRAW && !a.reset_noise)) {   // FishingModelError.reset, fishing_model_error.py:41-48
       double zK, zr;
       if (a.reset_noise) {
         zK = a.reset_noise[i];
         zr = a.reset_noise[a.n + i];
       } else {
-        const Normal2 d = normal_pair(a.seed, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET);
+        const Normal2 d = normal_pair_keys(a.keys, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET);
         zK = d.z0;
         zr = d.z1;
       }
@@ -104,21 +104,59 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
     }
   }
   if (a.flags & STEP_FLAG_PDL) pdl_wait();
-  if (!live) return;
+  // the fishing-v4 kernel keeps idle lanes of the last warp alive: its reset draws are shared out over the warp below
+  if (!live && PM != P_PERENV) return;
 
   // ---- phase B: state written by the previous launch
-  const double2 s = reinterpret_cast<const double2*>(a.state_in)[j];
-  const int2 yr = reinterpret_cast<const int2*>(a.years)[j];
+  double2 s = make_double2(0.0, 0.0);
+  int2 yr = make_int2(0, 0);
   double2 Kv = make_double2(a.K, a.K), rv = make_double2(a.r, a.r);
-  if (PM == P_PERENV) {
-    Kv = reinterpret_cast<const double2*>(a.K_env)[j];
-    rv = reinterpret_cast<const double2*>(a.r_env)[j];
+  if (live) {
+    s = reinterpret_cast<const double2*>(a.state_in)[j];
+    yr = reinterpret_cast<const int2*>(a.years)[j];
+    if (PM == P_PERENV) {
+      Kv = reinterpret_cast<const double2*>(a.K_env)[j];
+      rv = reinterpret_cast<const double2*>(a.r_env)[j];
+    }
   }
   const int64_t i0 = 2 * (int64_t)j;
   int2 mdl = make_int2(0, 0);
-  if (GROWTH == G_MODEL) mdl = reinterpret_cast<const int2*>(a.model)[j];
-  const EnvResult e0 = advance<GROWTH, PM, ACT>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
-  const EnvResult e1 = advance<GROWTH, PM, ACT>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
+  if (GROWTH == G_MODEL && live) mdl = reinterpret_cast<const int2*>(a.model)[j];
+  EnvResult e0 = advance<GROWTH, PM, ACT, true>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
+  EnvResult e1 = advance<GROWTH, PM, ACT, true>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
+  if (PM == P_PERENV) {
+    if (!live) e0.reset_fired = e1.reset_fired = false;
+    if ((a.flags & FISHING_AUTO_RESET) && !a.reset_noise) {
+      // Warp-cooperative parameter redraw.  A reset needs a Philox block + Box-Muller (~200 instructions); left inside
+      // advance() every warp would execute that path twice per step (once per environment slot) as soon as ANY lane
+      // resets.  Instead the resets of the warp's 64 environments are numbered with ballots, lane k draws for reset
+      // number k (all in one pass unless more than 32 environments of the warp reset at once), and the owners fetch
+      // their (K, r) with shuffles.  Same draws as the per-lane path: ctr = (global env id, step), stream AUTORESET.
+      const unsigned full = 0xffffffffu;
+      const int lane = threadIdx.x & 31;
+      const unsigned m0 = __ballot_sync(full, e0.reset_fired), m1 = __ballot_sync(full, e1.reset_fired);
+      const int n0 = __popc(m0), total = n0 + __popc(m1);
+      const unsigned below = (1u << lane) - 1u;
+      const int job0 = __popc(m0 & below), job1 = n0 + __popc(m1 & below);
+      for (int base = 0; base < total; base += 32) {
+        const int k = base + lane;
+        double Kn = 0.0, rn = 0.0;
+        if (k < total) {
+          const bool second = k >= n0;
+          const int owner = (int)__fns(second ? m1 : m0, 0, (second ? k - n0 : k) + 1);
+          const uint64_t gid = (uint64_t)(a.env_id0 + 2 * ((int64_t)j - lane + owner) + (second ? 1 : 0));
+          const Normal2 d = normal_pair_keys(a.keys, gid, a.step_idx, FISHING_STREAM_AUTORESET);
+          Kn = v4_param(a.K_mean, a.sigma_p, d.z0);
+          rn = v4_param(a.r_mean, a.sigma_p, d.z1);
+        }
+        const double K0 = __shfl_sync(full, Kn, (job0 - base) & 31), r0 = __shfl_sync(full, rn, (job0 - base) & 31);
+        const double K1 = __shfl_sync(full, Kn, (job1 - base) & 31), r1 = __shfl_sync(full, rn, (job1 - base) & 31);
+        if (e0.reset_fired && job0 >= base && job0 < base + 32) { e0.K = K0; e0.r = r0; }
+        if (e1.reset_fired && job1 >= base && job1 < base + 32) { e1.K = K1; e1.r = r1; }
+      }
+    }
+    if (!live) return;
+  }
   reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
   if (a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
   st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
