@@ -193,3 +193,14 @@ def test_gloo_world2_sharding_and_stats(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "ok 0" in res.stdout and "ok 1" in res.stdout
+
+
+def test_graft_entry_build_runs_here():
+    """The driver's "does it build" check: compiles (or finds up to date) the CUDA library and the oracle's C file."""
+    import importlib
+
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
+    from oracle.build_c import OUT
+
+    assert os.path.exists(OUT)
