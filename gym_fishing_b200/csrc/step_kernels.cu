@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
   const int64_t i0 = 2 * (int64_t)j;
   int2 mdl = make_int2(0, 0);
   if (GROWTH == G_MODEL && live) mdl = reinterpret_cast<const int2*>(a.model)[j];
-  EnvResult e0 = advance<GROWTH, PM, ACT, true>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
-  EnvResult e1 = advance<GROWTH, PM, ACT, true>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
+  EnvResult e0 = {}, e1 = {};   // idle lanes (fishing-v4 only, see above) never step and never reset
+  if (live) {
+    e0 = advance<GROWTH, PM, ACT, true>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
+    e1 = advance<GROWTH, PM, ACT, true>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
+  }
   if (PM == P_PERENV) {
-    if (!live) e0.reset_fired = e1.reset_fired = false;
     if ((a.flags & FISHING_AUTO_RESET) && !a.reset_noise) {
       // Warp-cooperative parameter redraw.  A reset needs a Philox block + Box-Muller (~200 instructions); left inside
       // advance() every warp would execute that path twice per step (once per environment slot) as soon as ANY lane

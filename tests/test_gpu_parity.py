@@ -669,3 +669,35 @@ def test_special_values_bitwise_against_oracle():
         for ret, ds, st in outs:
             assert np.array_equal(ret, e["ret"], equal_nan=True) and np.array_equal(ds, e["done_step"])
             assert np.array_equal(st, e["final_state"], equal_nan=True)
+
+
+@pytest.mark.parametrize("n", [66, 130, 4098])
+def test_v4_vector_path_with_partial_last_warp(n):
+    """fishing-v4 keeps the idle lanes of the last warp alive for the warp-cooperative reset draw; sizes that are even
+    (vector path) but not multiples of 64, with Philox and with injected reset noise."""
+    torch = _torch()
+    rng = np.random.default_rng(n)
+    T = 30
+    cfg = dict(r=0.3, K=1.0, sigma=0.05, x0=0.75, Tmax=6, sigma_p=0.2, seed=4)
+    acts = rng.uniform(-1.0, -0.3, size=(T, n))
+    from gym_fishing_b200 import _native as nat
+
+    for inject in (False, True):
+        b = make_batch("v4", n, auto_reset=True, **cfg)
+        rnoise = rng.standard_normal((T + 1, 2, n))
+        b.reset(reset_noise=dev(rnoise[0]) if inject else None)
+        K0, r0 = b.K_env.cpu().numpy().copy(), b.r_env.cpu().numpy().copy()
+        z = b.noise(T, step0=0).cpu().numpy()
+        if not inject:
+            rnoise = np.concatenate([np.zeros((1, 2, n)), b.noise(T, stream=nat.STREAM_AUTORESET, step0=0).cpu().numpy()])
+        obs = torch.empty(T, n, dtype=torch.float64, device="cuda")
+        rew = torch.empty_like(obs)
+        done = torch.empty(T, n, dtype=torch.uint8, device="cuda")
+        d_act, d_rn = dev(acts), dev(rnoise)
+        for t in range(T):
+            b.step(d_act[t], reset_noise=d_rn[t + 1] if inject else None, out_obs=obs[t], out_reward=rew[t], out_done=done[t])
+        exp = fo.rollout_vec("v4", T, n, r=r0, K=K0, sigma=0.05, x0=0.75, Tmax=6, policy="actions", actions=acts, noise=z,
+                             auto_reset=True, reset_noise=rnoise, K_mean=1.0, r_mean=0.3, sigma_p=0.2)
+        assert np.array_equal(done.cpu().numpy(), exp["done"]) and exp["done"].sum() > n
+        assert np.array_equal(obs.cpu().numpy(), exp["obs"]) and np.array_equal(rew.cpu().numpy(), exp["reward"])
+        assert np.array_equal(b.K_env.cpu().numpy(), exp["K"]) and np.array_equal(b.r_env.cpu().numpy(), exp["r"])
