@@ -149,14 +149,32 @@ __device__ __forceinline__ double grow_lognormal(double x1, const GrowthP& g, do
   return (0.0 > v) ? 0.0 : v;
 }
 
+// fishing-v11: the growth function differs from lane to lane, so a warp walks through up to five branches.  Four of the
+// five start from log(x) and all end in exp(mu + sigma z); those two calls are hoisted out of the divergent switch so
+// that each branch only holds its own few operations.  Same operations in the same order as lognormal_mu<FN>.
 __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP& g, double z, bool noisy) {
+  const double lx = log(x1);    // x1 >= +0 or NaN here, so Beverton-Holt's np.clip(x, 0, inf) is the identity
+  double mu;
   switch (fn) {
-    case FISHING_FN_ALLEN: return grow_lognormal<FISHING_FN_ALLEN>(x1, g, z, noisy);
-    case FISHING_FN_BEVERTON_HOLT: return grow_lognormal<FISHING_FN_BEVERTON_HOLT>(x1, g, z, noisy);
-    case FISHING_FN_MYERS: return grow_lognormal<FISHING_FN_MYERS>(x1, g, z, noisy);
-    case FISHING_FN_MAY: return grow_lognormal<FISHING_FN_MAY>(x1, g, z, noisy);
-    default: return grow_lognormal<FISHING_FN_RICKER>(x1, g, z, noisy);
+    case FISHING_FN_ALLEN:
+      mu = __dadd_rn(lx, div_z(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_z(x1, g.K))), g.omC), g.K));
+      break;
+    case FISHING_FN_BEVERTON_HOLT:
+      mu = __dsub_rn(__dadd_rn(g.logA, lx), log(__dadd_rn(1.0, div_z(x1, g.B))));
+      break;
+    case FISHING_FN_MYERS:
+      mu = __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, lx)), log(__dadd_rn(1.0, div_z(pow(x1, g.theta), g.M))));
+      break;
+    case FISHING_FN_MAY:
+      mu = lognormal_mu<FISHING_FN_MAY>(x1, g);
+      break;
+    default:
+      mu = __dadd_rn(lx, __dmul_rn(g.r, __dsub_rn(1.0, div_z(x1, g.K))));
+      break;
   }
+  if (noisy) mu = __dadd_rn(mu, __dmul_rn(g.sigma, z));
+  const double v = exp(mu);
+  return (0.0 > v) ? 0.0 : v;
 }
 
 template <int GROWTH>
