@@ -344,3 +344,27 @@ def test_render_file_logging_and_abi_error_codes(tmp_path):
     assert lib.fishing_vec_step(h, buf.ctypes.data, nat.ACT_F64, None, buf.ctypes.data, buf.ctypes.data, d8.ctypes.data, None) == -5
     assert lib.fishing_vec_reset(h, buf.ctypes.data) == 0 and buf[0] == -0.25
     assert lib.fishing_vec_destroy(h) == 0
+
+
+def test_integration_md_snippets_run(monkeypatch):
+    """The ctypes binding shown in INTEGRATION.md (sections 2 and 3) is executable as written."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(root)
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    ns = {}
+    exec(blocks[0], ns)                                   # section 2: fishing_reset + fishing_step on torch memory
+    import torch
+
+    torch.cuda.synchronize()
+    assert ns["rc"] == 0 and ns["done"].sum().item() > 0 and torch.isfinite(ns["state"]).all()
+    exec(blocks[1], ns)                                   # section 3: host-buffer VecEnv
+    v = ns["B200VecEnv"](64, sigma=0.0)
+    obs = v.reset()
+    assert obs.shape == (64, 1) and obs[0, 0] == -0.25
+    obs, rew, done, infos = v.step(np.full((64, 1), -0.9))
+    assert abs(rew[0] - 0.1) < 1e-12 and not done.any() and len(infos) == 64
+    v.close()
