@@ -52,3 +52,31 @@ def test_rollout_stats_cfg3_shape_at_test_size():
     assert abs(float(res["mean"]) - ret.mean()) <= 1e-12 * ret.mean()
     assert abs(float(res["std"]) - ret.std()) <= 1e-9
     assert float(res["n_done"]) == float((res["done_step"].cpu().numpy() >= 0).sum())
+
+
+def test_max_size_2pow24_shards_equal_whole_batch():
+    """BASELINE.json config 3 at its full per-box size (2^24 fishing-v2 envs) on one GPU for a few steps: eight shards with
+    global ids (what the 8 ranks run) reproduce the whole batch bit for bit, statistics included."""
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.distributed import tree_sum
+    from gym_fishing_b200.engine import EnvBatch
+
+    n, T, S = 1 << 24, 12, float.fromhex("0x1.9374bcp-1")
+    cfg = dict(r=0.3, K=1.0, sigma=0.05, C=0.5, x0=0.75, Tmax=1000, seed=0)
+    whole = EnvBatch(nat.V2, n, **cfg)
+    whole.reset()
+    out = whole.rollout(T, policy="escapement", S=S, freeze_done=True)
+    stats = whole.reduce_stats(out["ret"], out["done_step"], groups=256)
+    parts = []
+    shard = n // 8
+    for g in range(8):
+        b = EnvBatch(nat.V2, shard, env_id0=g * shard, **cfg)
+        b.reset()
+        o = b.rollout(T, policy="escapement", S=S, freeze_done=True)
+        assert torch.equal(o["ret"], out["ret"][g * shard:(g + 1) * shard])
+        assert torch.equal(b.state, whole.state[g * shard:(g + 1) * shard])
+        parts.append(b.reduce_stats(o["ret"], o["done_step"], groups=256))
+    assert torch.equal(tree_sum(parts), stats)
+    assert float(stats[:, 0].sum()) > 0 and torch.isfinite(whole.state).all()
