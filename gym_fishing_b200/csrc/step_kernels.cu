@@ -70,7 +70,7 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
 
 // ------------------------------------------------------------------------------------------------ K1, vector path
 // One thread owns ONE PAIR of adjacent environments (2j, 2j+1): 16-byte loads/stores on the float64 arrays, one Philox
-// block + one Box-Muller for the pair.  128-thread blocks, one pair per thread -> 4096 blocks at n = 2^20: fine-grained
+// block + one Box-Muller for the pair.  256-thread blocks, one pair per thread -> 2048 blocks at n = 2^20: fine-grained
 // enough that the tail of launch t is filled by the head of launch t+1 when programmatic dependent launch is on.
 //
 // The kernel has two phases.  Phase A touches only this launch's own inputs (actions, injected noise) and does all the
@@ -81,12 +81,12 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int GROWTH, int PM, int ACT>
-__global__ void __launch_bounds__(128) step_kernel_vec2(const StepArgs a) {
+template <int GROWTH, int PM, int ACT, int BS = 128>
+__global__ void __launch_bounds__(BS) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
   const int npairs = (int)(a.n >> 1);
-  const int j = (int)(blockIdx.x * 128u + threadIdx.x);
+  const int j = (int)(blockIdx.x * (unsigned)BS + threadIdx.x);
   const bool live = j < npairs;
   const bool ext_noise = a.noise != nullptr;
   const bool noisy = ext_noise || a.sigma != 0.0;
@@ -405,13 +405,13 @@ template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
   if (vec) {
     const int64_t npairs = a.n >> 1;
-    const int64_t blocks = (npairs + 127) / 128;
+    const int64_t blocks = (npairs + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (a.flags & STEP_FLAG_PDL) {
       // programmatic dependent launch: this grid may start while the previous kernel in the stream is still draining
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)blocks);
-      cfg.blockDim = dim3(128);
+      cfg.blockDim = dim3(256);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
@@ -420,9 +420,9 @@ static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       count_launch();
-      return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT>, a);
+      return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256>, a);
     }
-    step_kernel_vec2<GROWTH, PM, ACT><<<(unsigned)blocks, 128, 0, st>>>(a);
+    step_kernel_vec2<GROWTH, PM, ACT, 256><<<(unsigned)blocks, 256, 0, st>>>(a);
   } else {
     const int grid = grid_for(a.n, 256, 8);
     step_kernel_scalar<GROWTH, PM, ACT><<<grid, 256, 0, st>>>(a);
