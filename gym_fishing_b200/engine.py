@@ -233,6 +233,12 @@ class EnvBatch:
                 out_done_step=None):
         """fishing_rollout: T fused steps.  Returns dict(ret, done_step[, obs, reward, done, action])."""
         torch = self.torch
+        if self.n % 2 or self.env_id0 % 2:
+            raise ValueError("the fused rollout kernel owns environments in pairs: n and env_id0 must be even "
+                             f"(got n={self.n}, env_id0={self.env_id0}); use step()/step_many() for odd batches")
+        if noise_id_div and noise_id_div > 1 and (self.n % (2 * noise_id_div) or self.env_id0 % (2 * noise_id_div)):
+            raise ValueError("with noise_id_div = m the batch must hold whole pairs of noise ids: n and env_id0 must be "
+                             f"multiples of 2*m (got n={self.n}, env_id0={self.env_id0}, m={noise_id_div})")
         a = nat.FishingRolloutArgs()
         a.T = int(T)
         a.step0 = self.step_idx

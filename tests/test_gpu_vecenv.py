@@ -391,3 +391,29 @@ def test_examples_run_and_ppo_improves():
     rets = mod.main(["--envs", "8192", "--iters", "25", "--steps", "64"])
     # constant escapement (the optimum) earns 7.67 per episode on this model, MSY 6.32; PPO passes MSY within seconds
     assert len(rets) >= 20 and max(rets[-3:]) > 6.3
+
+
+def test_small_and_odd_batches():
+    import torch
+
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.engine import EnvBatch
+
+    for n in (1, 2, 3, 7):
+        v = gf.FishingVecEnv("fishing-v1", num_envs=n, sigma=0.1, Tmax=4, seed=2)
+        big = gf.FishingVecEnv("fishing-v1", num_envs=8, sigma=0.1, Tmax=4, seed=2)
+        o, ob = v.reset(), big.reset()
+        for t in range(9):
+            a = torch.full((8, 1), -0.8 + 0.01 * t, dtype=torch.float64, device="cuda")
+            o, r, d, _ = v.step(a[:n])
+            ob, rb, db, _ = big.step(a)
+            assert torch.equal(o, ob[:n]) and torch.equal(r, rb[:n]) and torch.equal(d, db[:n])   # same global env ids
+    b = EnvBatch(1, 3)
+    b.reset()
+    with pytest.raises(ValueError, match="pairs"):
+        b.rollout(4, policy="escapement", S=0.5)
+    b = EnvBatch(1, 8)
+    b.reset()
+    with pytest.raises(ValueError, match="multiples"):
+        b.rollout(4, policy="escapement", S=0.5, noise_id_div=3)
+    assert b.rollout(0, policy="escapement", S=0.5)["ret"].abs().sum().item() == 0.0     # T = 0 is a no-op
