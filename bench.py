@@ -359,6 +359,27 @@ def run_gpu(args):
     for pa in (p_obs, p_rew, p_done):
         pa.free()
     venv.close()
+    # the same through the stable-baselines3 dtypes (float32 actions in; float32 obs + float32 reward + bool done out): 13
+    # instead of 25 bytes per env-step over PCIe.  Reported next to the float64 (reference-dtype) figure, which stays `value`.
+    venv32 = FishingVecEnv("fishing-v1", num_envs=n, device=dev, io="numpy", seed=0, auto_reset=True, env_id_offset=rank * n,
+                           sb3_dtypes=True, r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
+    venv32.reset()
+    p_act32 = _PinnedArray(chunk_T * n, np.float32)
+    a32 = p_act32.array.reshape(chunk_T, n)
+    a32[:] = h_act.astype(np.float32)
+    q_obs, q_rew, q_done = _PinnedArray(chunk_T * n, np.float32), _PinnedArray(chunk_T * n, np.float32), _PinnedArray(chunk_T * n, np.uint8)
+    outs32 = (q_obs.array.reshape(chunk_T, n), q_rew.array.reshape(chunk_T, n), q_done.array.reshape(chunk_T, n))
+    venv32.step_many(a32, out=outs32)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_T // chunk_T):
+        venv32.step_many(a32, out=outs32)
+    torch.cuda.synchronize()
+    e2e32_ms = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev)
+    e2e32_value = world * n * e2e_T / (e2e32_ms * 1e-3)
+    venv32.close()
+    for pa in (p_act32, q_obs, q_rew, q_done):
+        pa.free()
     pinned.free()
 
     if rank == 0:
@@ -391,7 +412,9 @@ def run_gpu(args):
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
                     "lock_steps_timed": e2e_T,
                     "api": "FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, 8 lock-steps per call)",
-                    "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"}},
+                    "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"},
+                    "sb3_dtypes": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 9,
+                                   "api": "FishingVecEnv(io='numpy', sb3_dtypes=True).step_many -> fishing_vec_step_many_f32 (float32 actions / obs / rewards, the dtypes a stable-baselines3 VecEnv exchanges)"}},
             "fused": fused,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),

@@ -32,7 +32,7 @@ EXPORTS = (
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
-    "fishing_reset_models", "fishing_population_draw_ln",
+    "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32",
 )
 
 
@@ -103,6 +103,8 @@ def lib():
     L.fishing_step_many.argtypes = [P, i64, i64, u64, i64, vp, i32, vp, FishingSoA, vp, vp, vp, vp, vp]
     L.fishing_vec_step_many.restype = C.c_int
     L.fishing_vec_step_many.argtypes = [vp, i64, vp, i32, vp, vp, vp]
+    L.fishing_vec_step_many_f32.restype = C.c_int
+    L.fishing_vec_step_many_f32.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     L.fishing_vec_fetch_terminal.restype = C.c_int
     L.fishing_vec_fetch_terminal.argtypes = [vp, vp]
     L.fishing_noise_fill.restype = C.c_int

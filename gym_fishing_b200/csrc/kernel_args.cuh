@@ -38,6 +38,8 @@ struct StepArgs {
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
   double* __restrict__ out_obs2;     // optional second copy of the observations (zero-copy host front end: out_obs is
                                      // the device state, out_obs2 a device-mapped pinned host array)
+  float* __restrict__ out_obs_f32;   // optional float32 copies (what stable-baselines3's VecEnv buffers hold: the declared
+  float* __restrict__ out_reward_f32;  // observation space is float32 and DummyVecEnv stores rewards as float32)
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
   int32_t derive_on_device;          // fishing-v10: recompute gp's derived fields with the device's log (like K2 does)

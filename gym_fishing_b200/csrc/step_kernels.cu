@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(BS) step_kernel_vec2(const StepArgs a) {
   }
   reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
   if (a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
+  if (a.out_obs_f32) st_stream(reinterpret_cast<float2*>(a.out_obs_f32) + j, make_float2((float)e0.obs, (float)e1.obs));
+  if (a.out_reward_f32)
+    st_stream(reinterpret_cast<float2*>(a.out_reward_f32) + j, make_float2((float)e0.reward, (float)e1.reward));
   st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
   st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
   reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
@@ -203,6 +206,8 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
                                                  a.years[i], K, r, GROWTH == G_MODEL ? a.model[i] : 0);
     a.out_obs[i] = e.obs;
     if (a.out_obs2) a.out_obs2[i] = e.obs;
+    if (a.out_obs_f32) a.out_obs_f32[i] = (float)e.obs;
+    if (a.out_reward_f32) a.out_reward_f32[i] = (float)e.reward;
     a.out_reward[i] = e.reward;
     a.out_done[i] = e.done;
     a.years[i] = e.years;

@@ -172,9 +172,12 @@ class _PinnedArray:
 
 class FishingVecEnv:
     def __init__(self, env_id="fishing-v1", num_envs=1, *, device="cuda", io="torch", seed=0, auto_reset=True,
-                 env_id_offset=0, monitor=False, **env_kwargs):
+                 env_id_offset=0, monitor=False, sb3_dtypes=False, **env_kwargs):
         """monitor=True (torch mode): keep per-env episode return / length on the device and report them in
-        infos[i]["episode"] = {"r", "l"} when an episode ends, like stable-baselines3's VecMonitor."""
+        infos[i]["episode"] = {"r", "l"} when an episode ends, like stable-baselines3's VecMonitor.
+        sb3_dtypes=True: observations and rewards come back as float32, which is what a stable-baselines3 VecEnv hands
+        to the learner (the observation space is declared float32 and DummyVecEnv stores rewards in a float32 buffer);
+        the state itself stays float64 on the device.  In numpy mode this halves the PCIe traffic."""
         if env_id not in nat.KIND_OF_ID:
             raise KeyError(f"unknown environment id {env_id!r}")
         if io not in ("torch", "numpy"):
@@ -194,6 +197,7 @@ class FishingVecEnv:
         self.action_space = Discrete(self.cfg["n_actions"]) if self.kind == nat.V0 else unit_box()
         self.metadata = {"render.modes": ["human"]}
         self._pending = None
+        self.sb3_dtypes = bool(sb3_dtypes)
         self.monitor = bool(monitor)
         if self.monitor and io != "torch":
             raise ValueError("monitor=True needs io='torch'")
@@ -245,6 +249,8 @@ class FishingVecEnv:
         self._h_sets = [(_PinnedArray(n, np.float64), _PinnedArray(n, np.float64), _PinnedArray(n, np.uint8)) for _ in range(2)]
         self._h_flip = 0
         self._h_obs, self._h_reward, self._h_done = self._h_sets[0]
+        self._h_sets32 = [(_PinnedArray(n, np.float32), _PinnedArray(n, np.float32), _PinnedArray(n, np.uint8)) for _ in range(2)] \
+            if self.sb3_dtypes else []
         self._h_term = _PinnedArray(n, np.float64)
         self._h_act = _PinnedArray(n, np.float64)  # staging for pageable / wrongly-typed actions (8 bytes per env)
 
@@ -258,9 +264,10 @@ class FishingVecEnv:
             if self.monitor:
                 self.ep_return.zero_()
                 self.ep_length.zero_()
-            return s.view(self.num_envs, 1)
+            return s.view(self.num_envs, 1).float() if self.sb3_dtypes else s.view(self.num_envs, 1)
         nat.check(nat.lib().fishing_vec_reset(self._handle, self._h_obs.array.ctypes.data), "fishing_vec_reset")
-        return self._h_obs.array.reshape(self.num_envs, 1)
+        obs = self._h_obs.array.reshape(self.num_envs, 1)
+        return obs.astype(np.float32) if self.sb3_dtypes else obs
 
     def step_async(self, actions):
         self._pending = actions
@@ -313,6 +320,8 @@ class FishingVecEnv:
             self.ep_return.masked_fill_(done_b, 0.0)
             self.ep_length.masked_fill_(done_b, 0)
             episode = (self.last_ep_return, self.last_ep_length)
+        if self.sb3_dtypes:
+            return obs.view(self.num_envs, 1).float(), rew.float(), done_b, LazyInfos(done, self.terminal_obs, episode)
         return obs.view(self.num_envs, 1), rew, done_b, LazyInfos(done, self.terminal_obs, episode)
 
     def step_into(self, actions, out_obs, out_reward, out_done, out_terminal=None, noise=None):
@@ -341,6 +350,14 @@ class FishingVecEnv:
                 adt = nat.ACT_F64
         a = np.ascontiguousarray(a.reshape(n))
         self._h_flip ^= 1
+        if self.sb3_dtypes:
+            o32, r32, d8 = self._h_sets32[self._h_flip]
+            rc = nat.lib().fishing_vec_step_many_f32(self._handle, 1, a.ctypes.data, adt, o32.array.ctypes.data,
+                                                     r32.array.ctypes.data, d8.array.ctypes.data)
+            nat.check(rc, "fishing_vec_step_many_f32")
+            self._steps_done += 1
+            done = d8.array.view(np.bool_)
+            return (o32.array.reshape(n, 1), r32.array, done, LazyInfos(done, _LazyTerminal(self) if self.auto_reset else None))
         self._h_obs, self._h_reward, self._h_done = self._h_sets[self._h_flip]
         rc = nat.lib().fishing_vec_step(self._handle, a.ctypes.data, adt, None, self._h_obs.array.ctypes.data,
                                         self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data, None)
@@ -377,11 +394,14 @@ class FishingVecEnv:
             adt = nat.ACT_F32 if a.dtype == np.float32 else nat.ACT_F64
             a = a if a.dtype == np.float32 else a.astype(np.float64, copy=False)
         a = np.ascontiguousarray(a.reshape(T, n))
+        fdt = np.float32 if self.sb3_dtypes else np.float64
         if out is None:
-            out = (np.empty((T, n)), np.empty((T, n)), np.empty((T, n), dtype=np.uint8))
+            out = (np.empty((T, n), dtype=fdt), np.empty((T, n), dtype=fdt), np.empty((T, n), dtype=np.uint8))
         obs, rew, done = out
-        rc = nat.lib().fishing_vec_step_many(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data,
-                                             done.ctypes.data)
+        if obs.dtype != fdt or rew.dtype != fdt:
+            raise TypeError(f"output arrays must be {np.dtype(fdt).name}")
+        fn = nat.lib().fishing_vec_step_many_f32 if self.sb3_dtypes else nat.lib().fishing_vec_step_many
+        rc = fn(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data, done.ctypes.data)
         nat.check(rc, "fishing_vec_step_many")
         self._steps_done += T
         return obs, rew, done.view(np.bool_)
@@ -476,7 +496,7 @@ class FishingVecEnv:
         if self._handle is not None:
             nat.lib().fishing_vec_destroy(self._handle)
             self._handle = None
-            for a in (*self._h_sets[0], *self._h_sets[1], self._h_term, self._h_act):
+            for a in (*self._h_sets[0], *self._h_sets[1], *(x for st in self._h_sets32 for x in st), self._h_term, self._h_act):
                 a.free()
 
     def __del__(self):  # pragma: no cover

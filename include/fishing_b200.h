@@ -278,6 +278,11 @@ int fishing_host_free(void* ptr);
  * consecutive steps are pipelined over the handle's streams (the host-side counterpart of fishing_step_many). */
 int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, double* obs_out,
                           double* reward_out, uint8_t* done_out);
+/* the same with the dtypes a stable-baselines3 VecEnv hands to the learner: observations and rewards as float32 (the
+ * declared observation space is float32, base_fishing_env.py:54-58, and DummyVecEnv keeps rewards in a float32 buffer); the
+ * state stays float64 on the device, the float32 values are its round-to-nearest casts.  Halves the PCIe traffic. */
+int fishing_vec_step_many_f32(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, float* obs_out,
+                              float* reward_out, uint8_t* done_out);
 /* terminal observations of the most recent step (valid where that step reported done), fetched on demand so that the
  * per-step device-to-host traffic stays at obs + reward + done */
 int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out);

@@ -417,3 +417,32 @@ def test_small_and_odd_batches():
     with pytest.raises(ValueError, match="multiples"):
         b.rollout(4, policy="escapement", S=0.5, noise_id_div=3)
     assert b.rollout(0, policy="escapement", S=0.5)["ret"].abs().sum().item() == 0.0     # T = 0 is a no-op
+
+
+def test_sb3_dtypes_are_the_float32_casts_of_the_float64_path():
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 5000, 20
+    rng = np.random.default_rng(3)
+    acts32 = rng.uniform(-1, -0.4, size=(T, n)).astype(np.float32)        # what an SB3 policy emits
+    ref = gf.FishingVecEnv("fishing-v1", num_envs=n, io="numpy", seed=5, sigma=0.1, Tmax=5)
+    a = gf.FishingVecEnv("fishing-v1", num_envs=n, io="numpy", seed=5, sigma=0.1, Tmax=5, sb3_dtypes=True)
+    b = gf.FishingVecEnv("fishing-v1", num_envs=n, io="numpy", seed=5, sigma=0.1, Tmax=5, sb3_dtypes=True)
+    c = gf.FishingVecEnv("fishing-v1", num_envs=n, io="torch", seed=5, sigma=0.1, Tmax=5, sb3_dtypes=True)
+    o0 = ref.reset()
+    assert a.reset().dtype == np.float32 and np.array_equal(a.reset(), o0.astype(np.float32))
+    b.reset(), c.reset()
+    obs64, rew64, done64 = ref.step_many(acts32)
+    obs, rew, done = a.step_many(acts32)
+    assert obs.dtype == np.float32 and rew.dtype == np.float32 and done.dtype == np.bool_
+    assert np.array_equal(obs, obs64.astype(np.float32)) and np.array_equal(rew, rew64.astype(np.float32))
+    assert np.array_equal(done, done64)
+    for t in range(T):
+        o, r, d, _ = b.step(acts32[t])
+        ot, rt, dt, _ = c.step(torch.as_tensor(acts32[t], device="cuda"))
+        assert o.dtype == np.float32 and np.array_equal(o[:, 0], obs[t]) and np.array_equal(r, rew[t]) and np.array_equal(d, done[t])
+        assert ot.dtype == torch.float32 and np.array_equal(ot.cpu().numpy()[:, 0], obs[t]) and np.array_equal(rt.cpu().numpy(), rew[t])
+    for v in (ref, a, b, c):
+        v.close()
