@@ -216,7 +216,8 @@ def workload_config(args, world):
                         "auto-reset, rollout-buffer outputs",
             "envs_per_gpu": args.envs, "T_lockstep_per_bench_step": args.T, "env": "fishing-v1", "sigma": CFG["sigma"],
             "r": CFG["r"], "K": CFG["K"], "x0": CFG["x0"], "Tmax": CFG["Tmax"], "parallelism": f"replicas x{world}",
-            "l2": "inputs+outputs per bench step (26 GB) >> 126 MB L2; no flush needed"}
+            "l2": "inputs+outputs per bench step (26 GB) >> 126 MB L2; no flush needed",
+            "launch": "stream" if getattr(args, "no_graph", False) else "cuda-graph replay of T K1 launches (programmatic dependent launch between them)"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -245,17 +246,34 @@ def run_gpu(args):
     batch = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
     batch.reset()
 
-    # capture T launches of K1 into one CUDA graph on a side stream (the kernels go to whatever stream is current)
+    # capture T launches of K1 into one CUDA graph on a side stream (the kernels go to whatever stream is current);
+    # --no-graph (or a failed capture) issues the same launches directly from fishing_step_many's C loop instead
     stream = torch.cuda.Stream(device=dev)
-    graph = torch.cuda.CUDAGraph()
+    graph = None
     with torch.cuda.stream(stream):
         batch.step_many(actions, obs, rew, done)  # warm-up outside capture (module load etc.)
         stream.synchronize()
         l0 = lib.fishing_launch_count()
-        with torch.cuda.graph(graph, stream=stream):
+        if not args.no_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    batch.step_many(actions, obs, rew, done)
+            except Exception as exc:  # noqa: BLE001
+                print(f"bench: CUDA-graph capture failed ({exc}); falling back to direct launches", file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
+        if graph is None:
+            l0 = lib.fishing_launch_count()
             batch.step_many(actions, obs, rew, done)
         launches_per_step = lib.fishing_launch_count() - l0
     torch.cuda.synchronize()
+
+    def one_bench_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            batch.step_many(actions, obs, rew, done)
 
     def barrier():
         if world > 1:
@@ -264,13 +282,13 @@ def run_gpu(args):
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            graph.replay()
+            one_bench_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clocks:
             e0.record(stream)
             for _ in range(args.steps):
-                graph.replay()
+                one_bench_step()
             e1.record(stream)
             barrier()
         ms = e0.elapsed_time(e1)
@@ -438,6 +456,7 @@ def main():
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=1_000_000)
     ap.add_argument("--ref-steps-per-core", dest="ref_steps_per_core", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the K1 launches directly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -207,20 +207,20 @@ static int reset_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint6
 static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                      int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                      double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
-                     double* out_obs2, float* out_obs_f32, float* out_reward_f32, void* stream);
+                     double* out_obs2, void* stream);
 
 int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                  int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                  double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
                  void* stream) {
   return step_impl(p, n, env_id0, step_idx, action, action_dtype, noise, reset_noise, soa, out_obs, out_reward, out_done,
-                   out_terminal, out_stock, out_harvest, nullptr, nullptr, nullptr, stream);
+                   out_terminal, out_stock, out_harvest, nullptr, stream);
 }
 
 static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                      int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                      double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
-                     double* out_obs2, float* out_obs_f32, float* out_reward_f32, void* stream) {
+                     double* out_obs2, void* stream) {
   if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind) || !action || !out_obs || !out_reward || !out_done)
     return FISHING_E_ARG;
   const int asz = act_size(action_dtype);
@@ -244,7 +244,6 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
   a.out_stock = out_stock; a.out_harvest = out_harvest;
   a.out_obs2 = out_obs2;
-  a.out_obs_f32 = out_obs_f32; a.out_reward_f32 = out_reward_f32;
   a.gp = growth_of(p);
   a.keys = philox_round_keys(p->seed);
   a.model = soa.model;
@@ -260,8 +259,7 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
              (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
-             (!out_harvest || aligned(out_harvest, 16)) && (!out_obs2 || aligned(out_obs2, 16)) &&
-             (!out_obs_f32 || aligned(out_obs_f32, 8)) && (!out_reward_f32 || aligned(out_reward_f32, 8));
+             (!out_harvest || aligned(out_harvest, 16)) && (!out_obs2 || aligned(out_obs2, 16));
   if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
   if (p->kind == FISHING_V11) vec = vec && aligned(soa.model, 8);
   if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
@@ -614,7 +612,7 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
         rc = step_impl(&q, v->n, v->env_id0, v->step_idx, static_cast<const char*>(d_act) + t * v->n * asz, action_dtype, nullptr,
                        nullptr, v->soa, v->soa.state, static_cast<double*>(d_rew) + t * v->n,
                        static_cast<uint8_t*>(d_done) + t * v->n, v->d_terminal, nullptr, nullptr,
-                       static_cast<double*>(d_obs) + t * v->n, nullptr, nullptr, st);
+                       static_cast<double*>(d_obs) + t * v->n, st);
         v->step_idx += 1;
         if (q.kind == FISHING_V10) {
           volatile double r_next = q.r + q.alpha;
@@ -698,8 +696,9 @@ int fishing_vec_step_many_f32(fishing_vec* v, int64_t T, const void* actions, in
       if (s.K_env) { s.K_env += off; s.r_env += off; }
       if (s.model) s.model += off;
       rc = step_impl(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, nullptr, nullptr, s, v->d_obs + off,
-                     v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, nullptr, v->d_obs32 + off,
-                     v->d_reward32 + off, st);
+                     v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, nullptr, st);
+      if (rc) break;
+      rc = (int)launch_cast_f32(v->d_obs + off, v->d_reward + off, v->d_obs32 + off, v->d_reward32 + off, len, st);
       if (rc) break;
       e = cudaMemcpyAsync(obs_out + t * n + off, v->d_obs32 + off, (size_t)len * 4, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess)

@@ -38,8 +38,6 @@ struct StepArgs {
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
   double* __restrict__ out_obs2;     // optional second copy of the observations (zero-copy host front end: out_obs is
                                      // the device state, out_obs2 a device-mapped pinned host array)
-  float* __restrict__ out_obs_f32;   // optional float32 copies (what stable-baselines3's VecEnv buffers hold: the declared
-  float* __restrict__ out_reward_f32;  // observation space is float32 and DummyVecEnv stores rewards as float32)
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
   int32_t derive_on_device;          // fishing-v10: recompute gp's derived fields with the device's log (like K2 does)
@@ -104,6 +102,7 @@ cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r
                           double z, void* out, cudaStream_t st);
 cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
                              cudaStream_t st);
+cudaError_t launch_cast_f32(const double* a, const double* b, float* a32, float* b32, int64_t n, cudaStream_t st);
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);
 int64_t reduce_scratch_doubles(int64_t n, int64_t groups);

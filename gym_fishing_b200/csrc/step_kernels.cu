@@ -161,9 +161,6 @@ __global__ void __launch_bounds__(BS) step_kernel_vec2(const StepArgs a) {
   }
   reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
   if (a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
-  if (a.out_obs_f32) st_stream(reinterpret_cast<float2*>(a.out_obs_f32) + j, make_float2((float)e0.obs, (float)e1.obs));
-  if (a.out_reward_f32)
-    st_stream(reinterpret_cast<float2*>(a.out_reward_f32) + j, make_float2((float)e0.reward, (float)e1.reward));
   st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
   st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
   reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
@@ -206,8 +203,6 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
                                                  a.years[i], K, r, GROWTH == G_MODEL ? a.model[i] : 0);
     a.out_obs[i] = e.obs;
     if (a.out_obs2) a.out_obs2[i] = e.obs;
-    if (a.out_obs_f32) a.out_obs_f32[i] = (float)e.obs;
-    if (a.out_reward_f32) a.out_reward_f32[i] = (float)e.reward;
     a.out_reward[i] = e.reward;
     a.out_done[i] = e.done;
     a.years[i] = e.years;
@@ -503,6 +498,23 @@ cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r
   const int grid = grid_for(n, 256, 8);
   if (f32) growth_kernel<float><<<grid, 256, 0, st>>>(kind, n, (const float*)x, r, K, C, sigma, z, (float*)out);
   else growth_kernel<double><<<grid, 256, 0, st>>>(kind, n, (const double*)x, r, K, C, sigma, z, (double*)out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// float32 copies of two float64 arrays (the stable-baselines3-dtype host front end).  Kept OUT of the step kernel on purpose:
+// two more optional outputs there cost 6 registers = one resident block per SM = 9 % of the headline throughput.
+__global__ void __launch_bounds__(256) cast_f32_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                        float* __restrict__ a32, float* __restrict__ b32, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    a32[i] = (float)a[i];
+    b32[i] = (float)b[i];
+  }
+}
+
+cudaError_t launch_cast_f32(const double* a, const double* b, float* a32, float* b32, int64_t n, cudaStream_t st) {
+  cast_f32_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(a, b, a32, b32, n);
   count_launch();
   return cudaGetLastError();
 }

@@ -204,3 +204,31 @@ def test_graft_entry_build_runs_here():
     from oracle.build_c import OUT
 
     assert os.path.exists(OUT)
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """Occupancy guard (no GPU needed: reads the cubin's resource usage).  The headline K1 instantiation must stay at <= 32
+    registers (8 resident 256-thread blocks per SM); a change that pushed it to 38 cost 9 % throughput.  No spills anywhere
+    on the hot kernels."""
+    import shutil
+
+    from gym_fishing_b200 import _native as nat
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", nat.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            name = line.split()[1].rstrip(":")
+        elif line.startswith("REG:") and name:
+            usage[name] = {k: int(v) for k, v in (kv.split(":") for kv in line.split() if ":" in kv and kv.split(":")[1].isdigit())}
+    k1 = [u for n, u in usage.items() if "step_kernel_vec2ILi0ELi0ELi0E" in n]     # <LOGISTIC, P_KONE, F64>
+    assert k1 and all(u["REG"] <= 32 and u["STACK"] == 0 for u in k1), k1
+    fast = [u for n, u in usage.items() if "rollout_fast_kernelILi0ELi0E" in n]
+    assert fast and all(u["REG"] <= 64 and u["STACK"] == 0 for u in fast), fast
+    sweep = [u for n, u in usage.items() if "rollout_sweep_kernelILi0ELi0E" in n]
+    assert sweep and all(u["REG"] <= 128 and u["STACK"] == 0 for u in sweep), sweep
