@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfishing_b200.so")
+# FISHING_B200_LIB selects another build of the same library (A/B runs of kernel variants); never a different backend.
+LIB_PATH = os.environ.get("FISHING_B200_LIB") or os.path.join(_HERE, "libfishing_b200.so")
 
 # enums (include/fishing_b200.h)
 V0, V1, V2, V4 = 0, 1, 2, 4

@@ -343,6 +343,7 @@ int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const f
   if (n == 0) return 0;
   RolloutArgs a;
   a.n = n; a.env_id0 = env_id0; a.T = r->T; a.step0 = r->step0; a.seed = p->seed;
+  a.keys = philox_round_keys(p->seed);
   a.r = p->r; a.K = p->K; a.sigma = p->sigma; a.C = p->C;
   a.s_reset = reset_state_value(p);
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;

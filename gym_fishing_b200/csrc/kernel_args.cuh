@@ -91,6 +91,7 @@ struct RolloutArgs {
   double alpha;                      // v10: r += alpha before every draw
   int32_t nonstationary;
   int32_t* model;
+  PhiloxKeys keys;                   // round keys of `seed` (the step-noise stream reads them from the constant bank)
   ModelTable tab;
 };
 

@@ -196,12 +196,11 @@ __device__ __forceinline__ void sincospi_02(double t, double& sn, double& cs) {
   const double c = FD_FMA(z, FD_FMA(z, pc, -0.5), 1.0);
   // t = q/2 + y:  q odd -> (sin, cos) = (+-cos, -+sin) of pi*y
   const bool swap = q & 1;
-  double a = swap ? c : s;
-  double b = swap ? s : c;
-  if (q & 2) a = -a;
-  if ((q + 1) & 2) b = -b;
-  sn = a;
-  cs = b;
+  const double a = swap ? c : s;
+  const double b = swap ? s : c;
+  // negation = flipping the sign bit of the high word (one shift + one 3-input logic op instead of DADD + 2 selects)
+  sn = __hiloint2double(__double2hiint(a) ^ ((q << 30) & 0x80000000), __double2loint(a));
+  cs = __hiloint2double(__double2hiint(b) ^ (((q + 1) << 30) & 0x80000000), __double2loint(b));
 }
 
 // Uniform integer in [0, n) from the first Philox word (fishing-v11 model draw, np.random.choice(models)):

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
       const double2 z = load2_stream<double2>(a.noise + t * a.n, L);
       z0 = z.x; z1 = z.y;
     } else if (noisy) {
-      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
       z0 = d.z0; z1 = d.z1;
     }
     double q0, q1;
@@ -311,9 +311,15 @@ struct FastEnv {
   bool frozen;
 };
 
-template <int GROWTH, int PM, int POLICY, bool NOISY>
+// What happens to an environment whose episode ended: it keeps stepping (the reference's behaviour when a caller ignores
+// `done`), it is reset in place (VecEnv semantics), or it is frozen (return statistics of first episodes).  A template
+// parameter, so that the plain loop carries no `frozen` tests and the compiler does not have to unswitch the loop.
+enum : int { M_PLAIN = 0, M_AUTO_RESET = 1, M_FREEZE = 2 };
+
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
-                                              uint64_t gid, bool auto_reset, bool freeze) {
+                                              uint64_t gid) {
+  constexpr bool auto_reset = MODE == M_AUTO_RESET, freeze = MODE == M_FREEZE;
   double x = __dadd_rn(e.s, 1.0);
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
   double quota;
@@ -369,7 +375,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
 }
 
-template <int GROWTH, int PM, int POLICY, bool NOISY>
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
 __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
@@ -389,8 +395,6 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
     noise_pair = ((uint64_t)a.env_id0 >> 1) + (uint64_t)tid;
   }
   const uint64_t gid0 = (uint64_t)(a.env_id0 + L.i0), gid1 = (uint64_t)(a.env_id0 + L.i1);
-  const bool auto_reset = a.flags & FISHING_AUTO_RESET;
-  const bool freeze = !auto_reset && (a.flags & FISHING_FREEZE_DONE);
 
   FastEnv e0, e1;
   {
@@ -430,12 +434,17 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
     if (POLICY == FISHING_POLICY_ACTIONS && t + 1 < T) act_next = load2_stream<double2>(act_base + (int64_t)(t + 1) * a.n, L);
     double z0 = 0.0, z1 = 0.0;
     if (NOISY) {
-      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
       z0 = d.z0; z1 = d.z1;
     }
-    if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY>(a, e0, act.x, z0, t, gid0, auto_reset, freeze);
-    if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY>(a, e1, act.y, z1, t, gid1, auto_reset, freeze);
-    if (freeze && e0.frozen && e1.frozen) break;
+    if (MODE == M_FREEZE) {
+      if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
+      if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
+      if (e0.frozen && e1.frozen) break;
+    } else {
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
+    }
   }
 
   store2<double2>(a.state, L, e0.s, e1.s);
@@ -454,15 +463,13 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
 // levels generates the pair's two normals once per step and applies them to 2*LV environments -- the Philox +
 // Box-Muller cost, more than half of the instructions of the plain kernel, is amortised LV times.  The levels of a thread
 // are strided by m/LV so that neighbouring threads touch neighbouring addresses.
-template <int GROWTH, int PM, bool NOISY, int LV>
+template <int GROWTH, int PM, bool NOISY, int LV, int MODE>
 __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = a.noise_id_div, mq = m / LV;
   if (tid >= (a.n >> 1) / LV) return;
   const int64_t kp = tid / mq, jq = tid - kp * mq;
   const uint64_t noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
-  const bool auto_reset = a.flags & FISHING_AUTO_RESET;
-  const bool freeze = !auto_reset && (a.flags & FISHING_FREEZE_DONE);
   FastEnv e[2 * LV];
   int64_t idx[2 * LV];
 #pragma unroll
@@ -487,16 +494,16 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
   for (int t = 0; t < T; ++t) {
     double z[2] = {0.0, 0.0};
     if (NOISY) {
-      const Normal2 d = normal_pair(a.seed, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
       z[0] = d.z0;
       z[1] = d.z1;
     }
-    bool all_frozen = freeze;
+    bool all_frozen = MODE == M_FREEZE;
 #pragma unroll
     for (int k = 0; k < 2 * LV; ++k) {
-      if (!e[k].frozen)
-        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY>(a, e[k], 0.0, z[k & 1], t, (uint64_t)(a.env_id0 + idx[k]),
-                                                                     auto_reset, freeze);
+      if (MODE != M_FREEZE || !e[k].frozen)
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e[k], 0.0, z[k & 1], t,
+                                                                           (uint64_t)(a.env_id0 + idx[k]));
       all_frozen = all_frozen && e[k].frozen;
     }
     if (all_frozen) break;
@@ -515,10 +522,32 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
   }
 }
 
+static int done_mode(const RolloutArgs& a) {
+  return (a.flags & FISHING_AUTO_RESET) ? M_AUTO_RESET : (a.flags & FISHING_FREEZE_DONE) ? M_FREEZE : M_PLAIN;
+}
+
+template <int GROWTH, int PM, int POLICY, bool NOISY>
+static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_t st) {
+  switch (done_mode(a)) {
+    case M_AUTO_RESET: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET><<<grid, block, 0, st>>>(a); break;
+    case M_FREEZE: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_FREEZE><<<grid, block, 0, st>>>(a); break;
+    default: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_PLAIN><<<grid, block, 0, st>>>(a); break;
+  }
+}
+
 template <int GROWTH, int PM, int POLICY>
 static void launch_fast_n(const RolloutArgs& a, bool noisy, int grid, int block, cudaStream_t st) {
-  if (noisy) rollout_fast_kernel<GROWTH, PM, POLICY, true><<<grid, block, 0, st>>>(a);
-  else rollout_fast_kernel<GROWTH, PM, POLICY, false><<<grid, block, 0, st>>>(a);
+  if (noisy) launch_fast_m<GROWTH, PM, POLICY, true>(a, grid, block, st);
+  else launch_fast_m<GROWTH, PM, POLICY, false>(a, grid, block, st);
+}
+
+template <int GROWTH, int PM, bool NOISY, int LV>
+static void launch_sweep_m(const RolloutArgs& a, int grid, int block, cudaStream_t st) {
+  switch (done_mode(a)) {
+    case M_AUTO_RESET: rollout_sweep_kernel<GROWTH, PM, NOISY, LV, M_AUTO_RESET><<<grid, block, 0, st>>>(a); break;
+    case M_FREEZE: rollout_sweep_kernel<GROWTH, PM, NOISY, LV, M_FREEZE><<<grid, block, 0, st>>>(a); break;
+    default: rollout_sweep_kernel<GROWTH, PM, NOISY, LV, M_PLAIN><<<grid, block, 0, st>>>(a); break;
+  }
 }
 
 template <int GROWTH, int PM>
@@ -533,8 +562,8 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   constexpr int SWEEP_LV = 4;
   if (fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && a.noise_id_div % SWEEP_LV == 0 && !sweep_plain()) {
     const int64_t sgrid = (threads / SWEEP_LV + block - 1) / block;
-    if (a.sigma != 0.0) rollout_sweep_kernel<GROWTH, PM, true, SWEEP_LV><<<(int)sgrid, block, 0, st>>>(a);
-    else rollout_sweep_kernel<GROWTH, PM, false, SWEEP_LV><<<(int)sgrid, block, 0, st>>>(a);
+    if (a.sigma != 0.0) launch_sweep_m<GROWTH, PM, true, SWEEP_LV>(a, (int)sgrid, block, st);
+    else launch_sweep_m<GROWTH, PM, false, SWEEP_LV>(a, (int)sgrid, block, st);
   } else if (fast) {
     const bool noisy = a.sigma != 0.0;
     switch (policy) {

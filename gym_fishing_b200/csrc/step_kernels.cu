@@ -81,8 +81,14 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Occupancy experiment knob for the per-environment-parameter (fishing-v4) instantiations: minimum resident 256-thread
+// blocks per SM (0 = let ptxas choose: 64 registers, 4 blocks).  See DESIGN.md section 10 for the measured outcome.
+#ifndef V4_MIN_BLOCKS
+#define V4_MIN_BLOCKS 0
+#endif
+
 template <int GROWTH, int PM, int ACT, int BS = 128>
-__global__ void __launch_bounds__(BS) step_kernel_vec2(const StepArgs a) {
+__global__ void __launch_bounds__(BS, (PM == P_PERENV && BS == 256) ? V4_MIN_BLOCKS : 0) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
   const int npairs = (int)(a.n >> 1);
