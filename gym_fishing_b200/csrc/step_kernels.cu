@@ -79,16 +79,11 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
 // launch in the stream, and waits for the previous launch only between the phases, so consecutive lock-steps overlap:
 // the next step's noise is generated while this step drains.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Occupancy experiment knob for the per-environment-parameter (fishing-v4) instantiations: minimum resident 256-thread
-// blocks per SM (0 = let ptxas choose: 64 registers, 4 blocks).  See DESIGN.md section 10 for the measured outcome.
-#ifndef V4_MIN_BLOCKS
-#define V4_MIN_BLOCKS 0
-#endif
-
 template <int GROWTH, int PM, int ACT, int BS = 128>
-__global__ void __launch_bounds__(BS, (PM == P_PERENV && BS == 256) ? V4_MIN_BLOCKS : 0) step_kernel_vec2(const StepArgs a) {
+__global__ void __launch_bounds__(BS) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
   const int npairs = (int)(a.n >> 1);
@@ -102,6 +97,20 @@ __global__ void __launch_bounds__(BS, (PM == P_PERENV && BS == 256) ? V4_MIN_BLO
   double2 z = make_double2(0.0, 0.0);
   if (live) {
     act = ld_stream(reinterpret_cast<const AT2*>(a.action) + j);
+    // Start pulling this thread's state lines towards the L2 now, so that phase B finds them close by instead of paying
+    // a full round trip after the wait (a second DRAM trip once the batch is past the L2 -- fishing-v4 carries 28 B of
+    // state per environment -- and the far-partition L2 latency below that).  The L2 is the coherence point, so a line
+    // prefetched before the previous launch has written it is still read correctly afterwards.  Measured on B200:
+    // fishing-v4 at 2^22 envs 7.94 -> 7.00 ms per 128 steps; fishing-v1 sigma = 0.01: 7.37 -> 6.89 us per launch at
+    // 2^20 envs, 60.4 -> 53.1 us at 2^23.  Without noise phase A is too short for the prefetch to pay for its issue slots.
+    if (PM == P_PERENV || noisy) {
+      prefetch_l2(reinterpret_cast<const double2*>(a.state_in) + j);
+      prefetch_l2(reinterpret_cast<const int2*>(a.years) + j);
+      if (PM == P_PERENV) {
+        prefetch_l2(reinterpret_cast<const double2*>(a.K_env) + j);
+        prefetch_l2(reinterpret_cast<const double2*>(a.r_env) + j);
+      }
+    }
     if (ext_noise) {
       z = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
     } else if (noisy) {
@@ -140,19 +149,26 @@ __global__ void __launch_bounds__(BS, (PM == P_PERENV && BS == 256) ? V4_MIN_BLO
       // resets.  Instead the resets of the warp's 64 environments are numbered with ballots, lane k draws for reset
       // number k (all in one pass unless more than 32 environments of the warp reset at once), and the owners fetch
       // their (K, r) with shuffles.  Same draws as the per-lane path: ctr = (global env id, step), stream AUTORESET.
+      // Job k -> owning environment slot goes through a per-warp table in shared memory (one byte store per reset, one
+      // byte load per job): the find-nth-set-bit alternative (__fns) is a ~100-instruction software loop.
+      __shared__ uint8_t s_owner[BS / 32][64];
       const unsigned full = 0xffffffffu;
-      const int lane = threadIdx.x & 31;
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       const unsigned m0 = __ballot_sync(full, e0.reset_fired), m1 = __ballot_sync(full, e1.reset_fired);
       const int n0 = __popc(m0), total = n0 + __popc(m1);
       const unsigned below = (1u << lane) - 1u;
       const int job0 = __popc(m0 & below), job1 = n0 + __popc(m1 & below);
+      if (total > 0) {
+        if (e0.reset_fired) s_owner[warp][job0] = (uint8_t)(2 * lane);
+        if (e1.reset_fired) s_owner[warp][job1] = (uint8_t)(2 * lane + 1);
+        __syncwarp();
+      }
       for (int base = 0; base < total; base += 32) {
         const int k = base + lane;
         double Kn = 0.0, rn = 0.0;
         if (k < total) {
-          const bool second = k >= n0;
-          const int owner = (int)__fns(second ? m1 : m0, 0, (second ? k - n0 : k) + 1);
-          const uint64_t gid = (uint64_t)(a.env_id0 + 2 * ((int64_t)j - lane + owner) + (second ? 1 : 0));
+          const int slot = s_owner[warp][k];   // 2 * owner lane + (second environment of the pair)
+          const uint64_t gid = (uint64_t)(a.env_id0 + 2 * ((int64_t)j - lane) + slot);
           const Normal2 d = normal_pair_keys(a.keys, gid, a.step_idx, FISHING_STREAM_AUTORESET);
           Kn = v4_param(a.K_mean, a.sigma_p, d.z0);
           rn = v4_param(a.r_mean, a.sigma_p, d.z1);
