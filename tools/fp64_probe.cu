@@ -9,15 +9,17 @@
 #include <cuda_runtime.h>
 
 constexpr int CH = 8;        // independent chains per thread
-constexpr int ITER = 4096;
+constexpr int ITER = 16384;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) probe(double* out, uint32_t* outi, long long* cyc, double a, double b, uint32_t k, int iters) {
   const long long c0 = clock64();
   double x[CH];
   uint32_t u[CH], v[CH];
+  float f[CH];
+  const float g = (float)b;
 #pragma unroll
-  for (int c = 0; c < CH; ++c) { x[c] = a + c + threadIdx.x; u[c] = k + c * 77u + threadIdx.x; v[c] = k * 3u + c; }
+  for (int c = 0; c < CH; ++c) { x[c] = a + c + threadIdx.x; u[c] = k + c * 77u + threadIdx.x; v[c] = k * 3u + c; f[c] = (float)c; }
 #pragma unroll 1
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -29,6 +31,9 @@ __global__ void __launch_bounds__(256) probe(double* out, uint32_t* outi, long l
 #define LOP3U_() asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(v[c]), "r"(k))
 #define LOP3V_() asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(u[c]), "r"(k))
 #define IMAD_() asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(k), "r"(v[c]))
+#define IMADW_() asm volatile("{.reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t;}" : "+r"(u[c]), "+r"(v[c]) : "r"(k))
+#define FSEL_() asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.f32 %0, %0, %2, p;}" : "+f"(f[c]) : "r"(k), "f"(g))
+#define DSETP_() asm volatile("{.reg .pred p; setp.gt.f64 p, %1, %2; selp.u32 %0, %0, %3, p;}" : "+r"(u[c]) : "d"(x[c]), "d"(b), "r"(k))
       if (MODE == 0) DFMA_();
       if (MODE == 1) DADD_();
       if (MODE == 2) DMUL_();
@@ -39,14 +44,52 @@ __global__ void __launch_bounds__(256) probe(double* out, uint32_t* outi, long l
       if (MODE == 7) IMAD_();
       if (MODE == 8) { DFMA_(); LOP3U_(); LOP3V_(); IMAD_(); }
       if (MODE == 9) { DFMA_(); LOP3U_(); DADD_(); LOP3V_(); }
+      if (MODE == 10) IMADW_();
+      if (MODE == 11) { DFMA_(); IMADW_(); }
+      if (MODE == 12) FSEL_();
+      if (MODE == 13) { DFMA_(); FSEL_(); }
+      if (MODE == 14) DSETP_();
+      if (MODE == 15) { DFMA_(); LOP3U_(); DADD_(); FSEL_(); IMADW_(); }   // K2-like mix: 2 fp64 : 2 alu : 1 imad.wide
+      if (MODE == 16) { DFMA_(); DADD_(); LOP3U_(); }                      // 2 fp64 : 1 alu
     }
   }
   const long long c1 = clock64();
   if (threadIdx.x == 0) cyc[blockIdx.x] = c1 - c0;
   double s = 0; uint32_t w = 0;
 #pragma unroll
-  for (int c = 0; c < CH; ++c) { s += x[c]; w ^= u[c] ^ v[c]; }
+  for (int c = 0; c < CH; ++c) { s += x[c]; w ^= u[c] ^ v[c] ^ __float_as_uint(f[c]); }
   if (s == 1.2345 || w == 0x12345u) { out[threadIdx.x] = s; outi[threadIdx.x] = w; }
+}
+
+// dependent-issue latency: one warp per SM, one chain
+template <int OP>
+__global__ void lat(double* out, long long* cyc, double a, double b, uint32_t k, int iters) {
+  double x = a + threadIdx.x; uint32_t u = k + threadIdx.x, v = k;
+  const long long c0 = clock64();
+#pragma unroll 16
+  for (int i = 0; i < iters; ++i) {
+    if (OP == 0) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(a), "d"(b));
+    if (OP == 1) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(x) : "d"(b));
+    if (OP == 2) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(x) : "d"(a));
+    if (OP == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u) : "r"(v), "r"(k));
+    if (OP == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u) : "r"(k), "r"(v));
+    if (OP == 5) asm volatile("{.reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t;}" : "+r"(u), "+r"(v) : "r"(k));
+  }
+  const long long c1 = clock64();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = c1 - c0;
+  if (x == 1.2345 || (u ^ v) == 0x12345u) out[threadIdx.x] = x + u;
+}
+
+static void latency(double mhz) {
+  double* out; long long* cyc; long long h;
+  cudaMalloc(&out, 4096 * 8); cudaMalloc(&cyc, 8192 * 8);
+  const int iters = 1 << 16;
+  const char* names[6] = {"DFMA", "DADD", "DMUL", "LOP3", "IMAD", "IMAD.WIDE"};
+#define LAT(OP) lat<OP><<<1, 32>>>(out, cyc, 1.0000001, 1e-9, 0x9E3779B9u, iters); cudaDeviceSynchronize(); \
+  lat<OP><<<1, 32>>>(out, cyc, 1.0000001, 1e-9, 0x9E3779B9u, iters); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+  printf("dependent-issue latency %-10s %.2f cycles\n", names[OP], (double)h / iters);
+  LAT(0) LAT(1) LAT(2) LAT(3) LAT(4) LAT(5)
+  cudaFree(out); cudaFree(cyc);
 }
 
 template <int MODE>
@@ -97,5 +140,13 @@ int main() {
   run<5>("DFMA+IMAD", 1, 1, sms, mhz);
   run<8>("DFMA+2LOP3+IMAD", 1, 3, sms, mhz);
   run<9>("DFMA+LOP3+DADD+LOP3", 2, 2, sms, mhz);
+  run<10>("IMAD.WIDE", 0, 1, sms, mhz);
+  run<11>("DFMA+IMAD.WIDE", 1, 1, sms, mhz);
+  run<12>("ISETP+FSEL", 0, 2, sms, mhz);
+  run<13>("DFMA+ISETP+FSEL", 1, 2, sms, mhz);
+  run<14>("DSETP+SEL", 1, 1, sms, mhz);
+  run<15>("DFMA+LOP3+DADD+SETP+FSEL+IMAD.WIDE", 2, 4, sms, mhz);
+  run<16>("DFMA+DADD+LOP3", 2, 1, sms, mhz);
+  latency(mhz);
   return 0;
 }
