@@ -33,7 +33,7 @@ EXPORTS = (
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
-    "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32",
+    "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32", "fishing_probe_fp64",
 )
 
 
@@ -92,6 +92,8 @@ def lib():
     L.fishing_error_string.argtypes = [C.c_int]
     L.fishing_launch_count.restype = u64
     L.fishing_launch_count.argtypes = []
+    L.fishing_probe_fp64.restype = C.c_int
+    L.fishing_probe_fp64.argtypes = [vp, i32, i32, vp]
     L.fishing_reset.restype = C.c_int
     L.fishing_reset.argtypes = [P, i64, i64, u64, vp, vp, FishingSoA, vp, vp]
     L.fishing_reset_models.restype = C.c_int

@@ -155,6 +155,11 @@ int fishing_abi_version(void) { return FISHING_ABI_VERSION; }
 
 uint64_t fishing_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int fishing_probe_fp64(double* scratch, int32_t blocks, int32_t iters, void* stream) {
+  if (!scratch || blocks <= 0 || iters <= 0) return FISHING_E_ARG;
+  return (int)launch_fp64_probe(scratch, blocks, iters, (cudaStream_t)stream);
+}
+
 const char* fishing_error_string(int code) {
   switch (code) {
     case 0: return "ok";

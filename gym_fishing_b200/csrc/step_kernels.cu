@@ -541,6 +541,30 @@ cudaError_t launch_cast_f32(const double* a, const double* b, float* a32, float*
   return cudaGetLastError();
 }
 
+// FP64-pipe peak probe (measurement aid for the K2 roofline, SURVEY.md section 8d "measure with a DFMA loop"): every
+// thread runs `iters` rounds of 8 independent DFMA chains; 16 warps per SM sub-partition keep the pipe saturated.
+// Total DFMA warp-instructions = blocks * 8 warps * iters * 8; the caller times the launch with events.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, double a, double b, int iters) {
+  double x[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) x[c] = a + (double)(c + (int)threadIdx.x);
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[c]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += x[c];
+  if (s == 1.2345) out[threadIdx.x] = s;   // never true: keeps the chains alive
+}
+
+cudaError_t launch_fp64_probe(double* scratch, int blocks, int iters, cudaStream_t st) {
+  fp64_probe_kernel<<<blocks, 256, 0, st>>>(scratch, 1.0000001, 1e-9, iters);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st) {
   if (f64) bmsy_kernel<double><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);
   else bmsy_kernel<float><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);

@@ -138,6 +138,14 @@ const char* fishing_error_string(int code);
 uint64_t fishing_launch_count(void);
 
 /*
+ * Measurement aid (no reference counterpart): one launch of `blocks` x 256 threads, each running `iters` rounds of 8
+ * independent double-precision FMA chains = blocks * 8 * iters * 8 DFMA warp-instructions.  Timed by the caller with
+ * events, it gives the FP64-pipe peak that the fused rollout kernel's roofline is quoted against (bench.py).
+ * `scratch` is a device array of >= 256 doubles (never written in practice).
+ */
+int fishing_probe_fp64(double* scratch, int32_t blocks, int32_t iters, void* stream);
+
+/*
  * reset -- BaseFishingEnv.reset (base_fishing_env.py:83-91), FishingModelError.reset / __init__ draws
  * (fishing_model_error.py:35-48).  `mask` (uint8[n], NULL = all) selects environments.  v4 draws K then r per
  * env from reset_noise[0..n) and reset_noise[n..2n) when given, else from Philox stream FISHING_STREAM_RESET

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) probe(double* out, uint32_t* outi, long l
 #define LOP3V_() asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(u[c]), "r"(k))
 #define IMAD_() asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(k), "r"(v[c]))
 #define IMADW_() asm volatile("{.reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t;}" : "+r"(u[c]), "+r"(v[c]) : "r"(k))
+#define IMADHI_() asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[c]) : "r"(k))
+#define IMADLO_() asm volatile("mul.lo.u32 %0, %0, %1;" : "+r"(u[c]) : "r"(k))
 #define FSEL_() asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.f32 %0, %0, %2, p;}" : "+f"(f[c]) : "r"(k), "f"(g))
 #define DSETP_() asm volatile("{.reg .pred p; setp.gt.f64 p, %1, %2; selp.u32 %0, %0, %3, p;}" : "+r"(u[c]) : "d"(x[c]), "d"(b), "r"(k))
       if (MODE == 0) DFMA_();
@@ -51,6 +53,9 @@ __global__ void __launch_bounds__(256) probe(double* out, uint32_t* outi, long l
       if (MODE == 14) DSETP_();
       if (MODE == 15) { DFMA_(); LOP3U_(); DADD_(); FSEL_(); IMADW_(); }   // K2-like mix: 2 fp64 : 2 alu : 1 imad.wide
       if (MODE == 16) { DFMA_(); DADD_(); LOP3U_(); }                      // 2 fp64 : 1 alu
+      if (MODE == 17) IMADHI_();
+      if (MODE == 18) { IMADLO_(); IMADHI_(); }
+      if (MODE == 19) { DFMA_(); LOP3U_(); DADD_(); FSEL_(); IMADLO_(); IMADHI_(); }   // the mix of mode 15 with the wide multiply split
     }
   }
   const long long c1 = clock64();
@@ -147,6 +152,9 @@ int main() {
   run<14>("DSETP+SEL", 1, 1, sms, mhz);
   run<15>("DFMA+LOP3+DADD+SETP+FSEL+IMAD.WIDE", 2, 4, sms, mhz);
   run<16>("DFMA+DADD+LOP3", 2, 1, sms, mhz);
+  run<17>("IMAD.HI", 0, 1, sms, mhz);
+  run<18>("IMAD.LO+IMAD.HI", 0, 2, sms, mhz);
+  run<19>("DFMA+LOP3+DADD+SETP+FSEL+IMAD.LO+IMAD.HI", 2, 5, sms, mhz);
   latency(mhz);
   return 0;
 }
