@@ -42,6 +42,17 @@ UNIT = "env-steps/s"
 K1_BYTES = 41
 
 
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """Write the result line to the real stdout (see main(): file descriptor 1 itself is pointed at stderr)."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -209,7 +220,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -465,7 +476,7 @@ def run_gpu(args):
             "clocks": clocks.summary(),
             "check": {"frac_done_last_step": frac_done, "mean_reward_last_step": mean_rew},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -486,6 +497,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue the K1 launches directly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints
+    # "NCCL version ..." there when NCCL_DEBUG=VERSION is set on the box) are pointed at stderr for the whole run, and the
+    # line goes out through a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
