@@ -375,6 +375,12 @@ def run_gpu(args):
 
     # ---- e2e: numpy host buffers through the C-ABI host front end (H2D of actions, D2H of obs/reward/done every lock-step)
     e2e_T = min(T, args.e2e_T)
+    # host side of the copies: run on (and allocate the pinned buffers from) the cores next to this GPU; undone before the
+    # CPU baseline below, which must see every core of the box
+    from gym_fishing_b200.distributed import bind_cpu_to_gpu
+
+    affinity0 = os.sched_getaffinity(0)
+    bound_cpus = 0 if args.no_cpu_bind else bind_cpu_to_gpu(local)
     venv = FishingVecEnv("fishing-v1", num_envs=n, device=dev, io="numpy", seed=0, auto_reset=True, env_id_offset=rank * n,
                          r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
     venv.reset()
@@ -437,6 +443,7 @@ def run_gpu(args):
     for pa in (p_act32, q_obs, q_rew, q_done):
         pa.free()
     pinned.free()
+    os.sched_setaffinity(0, affinity0)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -466,7 +473,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
-                    "lock_steps_timed": e2e_T,
+                    "lock_steps_timed": e2e_T, "host_cores_bound_to_gpu_numa_node": bound_cpus,
                     "api": "FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, 8 lock-steps per call)",
                     "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"},
                     "sb3_dtypes": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 9,
@@ -494,6 +501,7 @@ def main():
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=1_000_000)
     ap.add_argument("--ref-steps-per-core", dest="ref_steps_per_core", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-bind", action="store_true", help="do not pin the e2e section to the GPU-local cores")
     ap.add_argument("--no-graph", action="store_true", help="issue the K1 launches directly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
