@@ -25,13 +25,14 @@ static bool generic_only() {
   return on;
 }
 
-// FISHING_SWEEP_PLAIN=1 keeps sweeps on the one-pair-per-thread kernel (A/B checks of the amortised sweep kernel)
-static bool sweep_plain() {
-  static const bool on = [] {
+// A/B checks of the sweep kernels: FISHING_SWEEP_PLAIN=1 keeps sweeps on the one-pair-per-thread kernel, =2 on the
+// per-thread amortised kernel (LV levels per thread); default: the warp-cooperative kernel when the level count allows.
+static int sweep_mode() {
+  static const int mode = [] {
     const char* e = std::getenv("FISHING_SWEEP_PLAIN");
-    return e && e[0] && e[0] != '0';
+    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;
   }();
-  return on;
+  return mode;
 }
 
 // The two environments a thread owns.  Default layout: adjacent ids (2j, 2j+1) -> 16-byte vector accesses.
@@ -535,6 +536,81 @@ static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K2, warp-cooperative sweep
+// Same sweep layout, amortised across the WARP instead of across a thread's registers: a warp owns one replicate pair and
+// 32 consecutive levels (lane = level), so all 32 lanes need the same two normals at every step.  Lane l generates the
+// draw of step t0 + l; the 32 draws are then handed round with shuffles while the warp walks through steps t0 .. t0+31.
+// One Philox block + Box-Muller per thread every 32 steps instead of every step (or every step per 4 levels): the loop
+// body is the noise-free dynamics plus four SHFL, at the register count -- and occupancy -- of the plain kernel.
+template <int GROWTH, int PM, bool NOISY, int MODE>
+__global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutArgs a) {
+  const unsigned full = 0xffffffffu;
+  const int64_t m = a.noise_id_div;                      // levels, a multiple of 32
+  const int64_t warps_per_pair = m >> 5;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= ((a.n / m) >> 1) * warps_per_pair) return;  // whole warps only
+  const int64_t kp = gw / warps_per_pair;
+  const int64_t j = (gw - kp * warps_per_pair) * 32 + lane;
+  const int64_t i0 = (2 * kp) * m + j, i1 = i0 + m;
+  const uint64_t noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
+  const uint64_t gid0 = (uint64_t)(a.env_id0 + i0), gid1 = (uint64_t)(a.env_id0 + i1);
+  FastEnv e0, e1;
+  e0.s = a.state[i0]; e1.s = a.state[i1];
+  e0.years = a.years[i0]; e1.years = a.years[i1];
+  e0.K = PM == P_PERENV ? a.K_env[i0] : a.K; e1.K = PM == P_PERENV ? a.K_env[i1] : a.K;
+  e0.r = PM == P_PERENV ? a.r_env[i0] : a.r; e1.r = PM == P_PERENV ? a.r_env[i1] : a.r;
+  e0.S = a.S_env ? a.S_env[i0] : a.S; e1.S = a.S_env ? a.S_env[i1] : a.S;
+  e0.ret = e1.ret = 0.0;
+  e0.done_step = e1.done_step = -1;
+  e0.frozen = e1.frozen = false;
+  e0.quota_const = e1.quota_const = 0.0;
+  const int T = (int)a.T;
+  bool all_done = false;
+#pragma unroll 1
+  for (int t0 = 0; t0 < T && !all_done; t0 += 32) {
+    Normal2 d;
+    d.z0 = d.z1 = 0.0;
+    if (NOISY && t0 + lane < T)
+      d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)(t0 + lane), FISHING_STREAM_STEP);
+    const int nt = (T - t0 < 32) ? T - t0 : 32;
+#pragma unroll 1
+    for (int dt = 0; dt < nt; ++dt) {
+      double z0 = 0.0, z1 = 0.0;
+      if (NOISY) {
+        z0 = __shfl_sync(full, d.z0, dt);
+        z1 = __shfl_sync(full, d.z1, dt);
+      }
+      const int t = t0 + dt;
+      if (MODE != M_FREEZE || !e0.frozen)
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, z0, t, gid0);
+      if (MODE != M_FREEZE || !e1.frozen)
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, z1, t, gid1);
+      if (MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen)) {   // warp-uniform: the shuffles need every lane
+        all_done = true;
+        break;
+      }
+    }
+  }
+  a.state[i0] = e0.s; a.state[i1] = e1.s;
+  a.years[i0] = e0.years; a.years[i1] = e1.years;
+  if (PM == P_PERENV) {
+    a.K_env[i0] = e0.K; a.K_env[i1] = e1.K;
+    a.r_env[i0] = e0.r; a.r_env[i1] = e1.r;
+  }
+  if (a.out_return) { a.out_return[i0] = e0.ret; a.out_return[i1] = e1.ret; }
+  if (a.out_done_step) { a.out_done_step[i0] = e0.done_step; a.out_done_step[i1] = e1.done_step; }
+}
+
+template <int GROWTH, int PM, bool NOISY>
+static void launch_sweep_warp_m(const RolloutArgs& a, int grid, int block, cudaStream_t st) {
+  switch ((a.flags & FISHING_AUTO_RESET) ? M_AUTO_RESET : (a.flags & FISHING_FREEZE_DONE) ? M_FREEZE : M_PLAIN) {
+    case M_AUTO_RESET: rollout_sweep_warp_kernel<GROWTH, PM, NOISY, M_AUTO_RESET><<<grid, block, 0, st>>>(a); break;
+    case M_FREEZE: rollout_sweep_warp_kernel<GROWTH, PM, NOISY, M_FREEZE><<<grid, block, 0, st>>>(a); break;
+    default: rollout_sweep_warp_kernel<GROWTH, PM, NOISY, M_PLAIN><<<grid, block, 0, st>>>(a); break;
+  }
+}
+
 template <int GROWTH, int PM, int POLICY>
 static void launch_fast_n(const RolloutArgs& a, bool noisy, int grid, int block, cudaStream_t st) {
   if (noisy) launch_fast_m<GROWTH, PM, POLICY, true>(a, grid, block, st);
@@ -560,7 +636,12 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   const bool fast = !a.discrete && !tracing && !a.noise && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
   constexpr int SWEEP_LV = 4;
-  if (fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && a.noise_id_div % SWEEP_LV == 0 && !sweep_plain()) {
+  const bool sweep = fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && sweep_mode() != 1;
+  if (sweep && a.noise_id_div % 32 == 0 && sweep_mode() == 0) {
+    const int64_t wgrid = (threads + block - 1) / block;          // one thread per (replicate pair, level), whole warps
+    if (a.sigma != 0.0) launch_sweep_warp_m<GROWTH, PM, true>(a, (int)wgrid, block, st);
+    else launch_sweep_warp_m<GROWTH, PM, false>(a, (int)wgrid, block, st);
+  } else if (sweep && a.noise_id_div % SWEEP_LV == 0) {
     const int64_t sgrid = (threads / SWEEP_LV + block - 1) / block;
     if (a.sigma != 0.0) launch_sweep_m<GROWTH, PM, true, SWEEP_LV>(a, (int)sgrid, block, st);
     else launch_sweep_m<GROWTH, PM, false, SWEEP_LV>(a, (int)sgrid, block, st);

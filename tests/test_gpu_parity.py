@@ -618,6 +618,29 @@ def test_fast_rollout_kernel_equals_generic_kernel_with_philox(kind, cfg, mode, 
         assert (res[0][1] >= 0).any()
 
 
+@pytest.mark.parametrize("kind,cfg", [c for c in CASES if c[0] != "v0"])
+@pytest.mark.parametrize("mode", ["plain", "auto_reset", "freeze"])
+@pytest.mark.parametrize("levels", [32, 96, 8])
+def test_sweep_kernels_equal_generic_kernel(kind, cfg, mode, levels):
+    """Escapement sweeps with common random numbers: the warp-cooperative kernel (levels % 32 == 0: one replicate pair x 32
+    levels per warp, draws handed round with shuffles) and the per-thread amortised kernel (levels % 4 == 0) against the
+    generic traced kernel on the same Philox stream, every done-handling mode, T not a multiple of 32."""
+    torch = _torch()
+    reps, T = 6, 75
+    n = levels * reps
+    S_env = dev(np.tile(np.linspace(0.0, 1.1 * cfg["K"], levels), reps))
+    res = []
+    for traced in (True, False):
+        b = make_batch(kind, n, auto_reset=(mode == "auto_reset"), seed=17, **cfg)
+        b.reset()
+        out = b.rollout(T, policy="escapement", S_env=S_env, noise_id_div=levels, freeze_done=(mode == "freeze"), trace=traced)
+        res.append((out["ret"].clone(), out["done_step"].clone(), b.state.clone(), b.years.clone(),
+                    None if b.K_env is None else b.K_env.clone()))
+    for x, y in zip(*res):
+        if x is not None:
+            assert torch.equal(x, y), (kind, mode, levels)
+
+
 def test_special_values_bitwise_against_oracle():
     """NaN / inf / negative / signed-zero states, actions and noise through K1 (both paths) and K2: the comparisons
     removed from the kernels as provably redundant (max(x - h, 0), ...) must not change any bit on any input."""
