@@ -17,7 +17,7 @@ $NCU --set full --import-source on -k regex:step_kernel_vec2 --launch-skip 40 --
 # K2 fast path and the sweep kernel
 python tools/k2_bench.py > $OUT/plain_k2_$TAG.json 2> $OUT/plain_k2_$TAG.err || { echo "plain k2 failed"; exit 1; }
 K2B_T=200 $NCU --set full --import-source on -k regex:rollout_fast_kernel --launch-skip 2 --launch-count 2 -o $OUT/k2_$TAG -f python tools/k2_bench.py > $OUT/ncu_k2_$TAG.log 2>&1
-K2B_T=200 $NCU --set full --import-source on -k regex:rollout_sweep_kernel --launch-skip 2 --launch-count 1 -o $OUT/k2sweep_$TAG -f python tools/k2_bench.py > $OUT/ncu_k2s_$TAG.log 2>&1
+K2B_T=200 $NCU --set full --import-source on -k regex:rollout_sweep --launch-skip 2 --launch-count 1 -o $OUT/k2sweep_$TAG -f python tools/k2_bench.py > $OUT/ncu_k2s_$TAG.log 2>&1
 # fishing-v4 K1 at cfg-4 size (DRAM-resident state)
 python benchmarks/run_configs.py --only cfg4 > $OUT/plain_cfg4_$TAG.json 2> $OUT/plain_cfg4_$TAG.err || { echo "plain cfg4 failed"; exit 1; }
 $NCU --set full --import-source on -k regex:step_kernel_vec2 --launch-skip 300 --launch-count 2 -o $OUT/k1v4_$TAG -f python benchmarks/run_configs.py --only cfg4 > $OUT/ncu_k1v4_$TAG.log 2>&1
