@@ -68,6 +68,13 @@ __device__ __forceinline__ double div_z(double a, double b) {
   return (b == b && b != 0.0) ? signed_zero : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// The same for a divisor that is a constructor parameter and very often exactly 1 (the log-normal family's default K and
+// M): a / 1.0 is a for every a, so the division sequence (~25 instructions) is skipped behind a warp-uniform test.
+__device__ __forceinline__ double div_u(double a, double b) {
+  if (b == 1.0) return a;
+  return div_z(a, b);
+}
+
 // get_quota, base_fishing_env.py:135-147
 template <int PM>
 __device__ __forceinline__ double quota_f64(double a, double K) {
@@ -122,7 +129,7 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
 template <int FN>
 __device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
   if (FN == FISHING_FN_ALLEN) {            // np.log(x) + r * (1 - x / K) * (1 - C) / K
-    const double y = div_z(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_z(x, g.K))), g.omC), g.K);
+    const double y = div_u(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_u(x, g.K))), g.omC), g.K);
     return __dadd_rn(log(x), y);
   } else if (FN == FISHING_FN_BEVERTON_HOLT) {   // log(A) + log(x) - log(1 + x / B), A = r + 1, B = K / r
     const double xc = (x < 0.0) ? 0.0 : x;                       // np.clip(x, 0, inf)
@@ -134,9 +141,9 @@ __device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
     return log(e);
   } else if (FN == FISHING_FN_MYERS) {     // log(r + 1) + theta*log(x) - log(1 + x^theta / M)
     return __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, log(x))),
-                     log(__dadd_rn(1.0, div_z(pow(x, g.theta), g.M))));
+                     log(__dadd_rn(1.0, div_u(pow(x, g.theta), g.M))));
   } else {                                 // Ricker: log(x) + r * (1 - x / K)
-    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, div_z(x, g.K))));
+    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, div_u(x, g.K))));
   }
 }
 
@@ -157,19 +164,19 @@ __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP
   double mu;
   switch (fn) {
     case FISHING_FN_ALLEN:
-      mu = __dadd_rn(lx, div_z(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_z(x1, g.K))), g.omC), g.K));
+      mu = __dadd_rn(lx, div_u(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_u(x1, g.K))), g.omC), g.K));
       break;
     case FISHING_FN_BEVERTON_HOLT:
       mu = __dsub_rn(__dadd_rn(g.logA, lx), log(__dadd_rn(1.0, div_z(x1, g.B))));
       break;
     case FISHING_FN_MYERS:
-      mu = __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, lx)), log(__dadd_rn(1.0, div_z(pow(x1, g.theta), g.M))));
+      mu = __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, lx)), log(__dadd_rn(1.0, div_u(pow(x1, g.theta), g.M))));
       break;
     case FISHING_FN_MAY:
       mu = lognormal_mu<FISHING_FN_MAY>(x1, g);
       break;
     default:
-      mu = __dadd_rn(lx, __dmul_rn(g.r, __dsub_rn(1.0, div_z(x1, g.K))));
+      mu = __dadd_rn(lx, __dmul_rn(g.r, __dsub_rn(1.0, div_u(x1, g.K))));
       break;
   }
   if (noisy) mu = __dadd_rn(mu, __dmul_rn(g.sigma, z));
@@ -213,7 +220,9 @@ __device__ __forceinline__ StepOut step_core(double s, double quota, double z, d
   if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
   else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);
   StepOut o;
-  o.s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, K), 1.0);  // get_state :162-164
+  // get_state :162-164 (the log-normal family always takes the general-K path, with K = 1 by default: div_u)
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) o.s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, K), 1.0);
+  else o.s2 = __dsub_rn(div_u(x2, K), 1.0);
   o.reward = py_max(h, 0.0);                        // :74
   o.dead = x2 <= 0.0;                               // :78
   o.stock = x2;

@@ -432,8 +432,7 @@ static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
 
 template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
-  // the lean instantiation exists for the classic environments only (the log-normal family is bound by libdevice calls)
-  constexpr bool CAN_LEAN = GROWTH == LOGISTIC || GROWTH == TIPPING;
+  constexpr bool CAN_LEAN = true;
   const bool lean = CAN_LEAN && !a.noise && !a.reset_noise && !a.out_obs2 && !a.out_stock && !a.out_harvest && !a.out_terminal;
   if (vec) {
     const int64_t npairs = a.n >> 1;
