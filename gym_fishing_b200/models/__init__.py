@@ -1,1 +1,1 @@
-from .policies import BMSY, escapement, msy  # noqa: F401
+from .policies import BMSY, escapement, msy, user_action  # noqa: F401

@@ -67,3 +67,16 @@ class escapement:
     def predict(self, obs, **kwargs):
         x = self.env.get_fish_population(obs)
         return self.env.get_action(max(x - self.S, 0.0)), obs
+
+
+class user_action:
+    """Interactive policy: shows the stock and asks for a harvest quota on stdin (models/policies.py:34-48 of the
+    reference).  Host-side only -- the quota goes through the env's own get_action like any other policy."""
+
+    def __init__(self, env, **kwargs):
+        self.env = env
+
+    def predict(self, obs, **kwargs):
+        fish_population = self.env.get_fish_population(obs)
+        quota = input("fish population: " + str(fish_population) + ". Your harvest quota: ")
+        return self.env.get_action(float(quota)), obs

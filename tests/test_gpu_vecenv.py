@@ -446,3 +446,21 @@ def test_sb3_dtypes_are_the_float32_casts_of_the_float64_path():
         assert ot.dtype == torch.float32 and np.array_equal(ot.cpu().numpy()[:, 0], obs[t]) and np.array_equal(rt.cpu().numpy(), rew[t])
     for v in (ref, a, b, c):
         v.close()
+
+
+def test_user_action_policy_reads_a_quota_from_stdin(monkeypatch):
+    """models/policies.py:34-48 of the reference: prompt with the stock, parse the quota, map it through get_action."""
+    import builtins
+
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.models import user_action
+
+    for env_id, expect in (("fishing-v1", 0.2 / 1.0 - 1.0), ("fishing-v0", 20)):
+        env = gf.make(env_id)
+        obs = env.reset()
+        prompts = []
+        monkeypatch.setattr(builtins, "input", lambda prompt: (prompts.append(prompt), "0.2")[1])
+        action, state = user_action(env).predict(obs)
+        assert "fish population: 0.75" in prompts[0] and state is obs
+        assert action == expect
+        env.step(action)
