@@ -319,7 +319,7 @@ enum : int { M_PLAIN = 0, M_AUTO_RESET = 1, M_FREEZE = 2 };
 
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
-                                              uint64_t gid) {
+                                              uint64_t gid, double& reward_out, bool& done_out) {
   constexpr bool auto_reset = MODE == M_AUTO_RESET, freeze = MODE == M_FREEZE;
   double x = __dadd_rn(e.s, 1.0);
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
@@ -354,6 +354,8 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   const double reward = py_max(h, 0.0);
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;
+  reward_out = reward;
+  done_out = done;
   if (auto_reset || e.done_step < 0) e.ret = __dadd_rn(e.ret, reward);
   e.s = s2;
   if (done) {
@@ -377,6 +379,16 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
 }
 
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
+__device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
+                                              uint64_t gid) {
+  double reward;
+  bool done;
+  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e, action, z, t, gid, reward, done);
+}
+
+// TRACE: per-step observation / reward / done rows [T, n] written with streaming stores (the rollout-buffer fill of a
+// whole chunk in one launch).  Not combined with freeze-on-done or an action trace; those go to the generic kernel.
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
 __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
@@ -442,6 +454,15 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
       if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
       if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
       if (e0.frozen && e1.frozen) break;
+    } else if (TRACE) {
+      double r0, r1;
+      bool d0, d1;
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0, r0, d0);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1, r1, d1);
+      const int64_t off = (int64_t)t * a.n;
+      if (a.trace_obs) store2_stream<double2>(a.trace_obs + off, L, e0.s, e1.s);
+      if (a.trace_reward) store2_stream<double2>(a.trace_reward + off, L, r0, r1);
+      if (a.trace_done) store2_stream<uchar2>(a.trace_done + off, L, (uint8_t)d0, (uint8_t)d1);
     } else {
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
@@ -529,6 +550,13 @@ static int done_mode(const RolloutArgs& a) {
 
 template <int GROWTH, int PM, int POLICY, bool NOISY>
 static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_t st) {
+  if (a.trace_obs || a.trace_reward || a.trace_done) {
+    if constexpr (POLICY != FISHING_POLICY_MSY) {   // launch_rollout_p sends MSY + traces and freeze + traces elsewhere
+      if (done_mode(a) == M_AUTO_RESET) rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET, true><<<grid, block, 0, st>>>(a);
+      else rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_PLAIN, true><<<grid, block, 0, st>>>(a);
+    }
+    return;
+  }
   switch (done_mode(a)) {
     case M_AUTO_RESET: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET><<<grid, block, 0, st>>>(a); break;
     case M_FREEZE: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_FREEZE><<<grid, block, 0, st>>>(a); break;
@@ -633,7 +661,10 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   const int64_t grid = (threads + block - 1) / block;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   const bool tracing = a.trace_obs || a.trace_reward || a.trace_done || a.trace_action;
-  const bool fast = !a.discrete && !tracing && !a.noise && a.T <= 0x7fffffffLL &&
+  // traces ride on the specialised kernel unless they include the action trace, the done-handling is freeze-on-done, the
+  // policy is MSY, or the environments are laid out as a sweep
+  const bool fast_trace_ok = !a.trace_action && done_mode(a) != M_FREEZE && policy != FISHING_POLICY_MSY && a.noise_id_div <= 1;
+  const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
   constexpr int SWEEP_LV = 4;
   const bool sweep = fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && sweep_mode() != 1;

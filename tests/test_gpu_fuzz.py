@@ -150,7 +150,8 @@ def test_random_configuration_k2_against_oracle(seed):
         for traced in (True, False):
             bb = EnvBatch(KIND[kind], n, auto_reset=(mode == "auto_reset"), seed=seed, **cfg)
             bb.reset()
-            o = bb.rollout(T, policy=policy, S=S, msy_q=msy_q, actions=d_acts, freeze_done=(mode == "freeze"), trace=traced)
+            o = bb.rollout(T, policy=policy, S=S, msy_q=msy_q, actions=d_acts, freeze_done=(mode == "freeze"), trace=traced,
+                           trace_action=traced)   # the action trace keeps the traced leg on the generic kernel
             res.append((o["ret"].clone(), o["done_step"].clone(), bb.state.clone(), bb.years.clone(),
                         None if bb.K_env is None else bb.K_env.clone()))
         for x, y in zip(*res):

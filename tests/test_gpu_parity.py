@@ -332,7 +332,7 @@ def test_fused_rollout_matches_oracle_and_single_steps(kind, cfg, policy):
     b.reset(reset_noise=dev(rn0) if kind == "v4" else None)
     kw = dict(policy=policy, S=S, msy_q=msy_q,
               actions=dev(acts, torch.int64 if kind == "v0" else torch.float64) if policy == "actions" else None)
-    slow = b.rollout(T, trace=True, **kw)
+    slow = b.rollout(T, trace=True, trace_action=True, **kw)   # the action trace keeps this leg on the generic kernel
     fast = b2.rollout(T, **kw)
     assert torch.equal(slow["ret"], fast["ret"]) and torch.equal(slow["done_step"], fast["done_step"])
     assert torch.equal(b.state, b2.state) and torch.equal(b.years, b2.years)
@@ -609,7 +609,8 @@ def test_fast_rollout_kernel_equals_generic_kernel_with_philox(kind, cfg, mode, 
             b = make_batch(kind, n, auto_reset=(mode == "auto_reset"), seed=3, **cfg)
             b.reset()
             out = b.rollout(T, policy=policy, S=S, msy_q=float(np.float32(0.05 * cfg["K"])),
-                            actions=acts if policy == "actions" else None, freeze_done=(mode == "freeze"), trace=traced)
+                            actions=acts if policy == "actions" else None, freeze_done=(mode == "freeze"), trace=traced,
+                            trace_action=traced)   # the action trace keeps the traced leg on the generic kernel
             res.append((out["ret"].clone(), out["done_step"].clone(), b.state.clone(), b.years.clone(),
                         None if b.K_env is None else b.K_env.clone()))
         for x, y in zip(*res):
@@ -639,6 +640,44 @@ def test_sweep_kernels_equal_generic_kernel(kind, cfg, mode, levels):
     for x, y in zip(*res):
         if x is not None:
             assert torch.equal(x, y), (kind, mode, levels)
+
+
+@pytest.mark.parametrize("kind,cfg", [c for c in CASES if c[0] != "v0"])
+@pytest.mark.parametrize("auto_reset", [False, True])
+def test_traced_fast_rollout_equals_generic_traces_and_single_steps(kind, cfg, auto_reset):
+    """The specialised kernel with per-step observation / reward / done rows (the rollout-buffer fill of a whole chunk in
+    one launch) against the generic kernel's traces (forced by also asking for the action trace) and against T launches of
+    K1 on the same Philox stream: every row bit for bit."""
+    torch = _torch()
+    n, T = 4096, 130
+    rng = np.random.default_rng(23)
+    acts = dev(rng.uniform(-1.0, -0.5, size=(T, n)))
+    S = float(np.float32(0.45 * cfg["K"]))
+    for policy in ("actions", "escapement"):
+        outs = []
+        for generic in (True, False):
+            b = make_batch(kind, n, auto_reset=auto_reset, seed=9, **cfg)
+            b.reset()
+            o = b.rollout(T, policy=policy, S=S, actions=acts if policy == "actions" else None, trace=True, trace_action=generic)
+            outs.append((o, b.state.clone(), b.years.clone()))
+        (g, gs, gy), (f, fs, fy) = outs
+        for k in ("obs", "reward", "done", "ret", "done_step"):
+            a_, b_ = g[k], f[k]
+            if a_.dtype == torch.float64:
+                a_, b_ = a_.view(torch.int64), b_.view(torch.int64)
+            assert torch.equal(a_, b_), (kind, policy, auto_reset, k)
+        assert torch.equal(gs.view(torch.int64), fs.view(torch.int64)) and torch.equal(gy, fy)
+        assert bool(f["done"].any())
+        if policy == "actions":
+            b = make_batch(kind, n, auto_reset=auto_reset, seed=9, **cfg)
+            b.reset()
+            obs = torch.empty(T, n, dtype=torch.float64, device="cuda")
+            rew = torch.empty_like(obs)
+            done = torch.empty(T, n, dtype=torch.uint8, device="cuda")
+            for t in range(T):
+                b.step(acts[t], out_obs=obs[t], out_reward=rew[t], out_done=done[t])
+            assert torch.equal(obs.view(torch.int64), f["obs"].view(torch.int64))
+            assert torch.equal(rew.view(torch.int64), f["reward"].view(torch.int64)) and torch.equal(done, f["done"])
 
 
 def test_special_values_bitwise_against_oracle():
@@ -684,7 +723,7 @@ def test_special_values_bitwise_against_oracle():
             b = EnvBatch(1, n, r=0.3, K=K, sigma=0.0, Tmax=100, x0=0.75)
             b.reset()
             b.state.copy_(dev(s0))
-            out = b.rollout(6, policy="escapement", S=0.4 * K, trace=traced)
+            out = b.rollout(6, policy="escapement", S=0.4 * K, trace=traced, trace_action=traced)
             outs.append((out["ret"].cpu().numpy(), out["done_step"].cpu().numpy(), b.state.cpu().numpy()))
         with np.errstate(all="ignore"):
             e = fo.rollout_vec("v1", 6, n, r=0.3, K=K, sigma=0.0, x0=0.75, Tmax=100, policy="escapement", S=0.4 * K, s0=s0,
