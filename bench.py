@@ -319,12 +319,13 @@ def run_gpu(args):
         for name, kw in (("actions_tensor_with_trace", dict(trace=True)), ("actions_tensor_returns_only", dict())):
             b2 = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
             b2.reset()
-            b2.rollout(T, policy="actions", actions=actions, **kw)
+            out = b2.rollout(T, policy="actions", actions=actions, **kw)
             stream.synchronize()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 3
             f0.record(stream)
             for _ in range(reps):
+                out = None      # release the previous call's trace tensors first: no allocator growth inside the timed region
                 out = b2.rollout(T, policy="actions", actions=actions, **kw)
             f1.record(stream)
             stream.synchronize()

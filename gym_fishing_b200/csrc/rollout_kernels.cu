@@ -440,6 +440,10 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
   const double* act_base = reinterpret_cast<const double*>(a.actions);
   double2 act_next = make_double2(0.0, 0.0);
   if (POLICY == FISHING_POLICY_ACTIONS && T > 0) act_next = load2_stream<double2>(act_base, L);
+  const int64_t row_f64 = a.n * 8, row_u8 = a.n;   // one trace row, in bytes
+  char* tr_obs = TRACE ? reinterpret_cast<char*>(a.trace_obs) + tid * 16 : nullptr;
+  char* tr_rew = TRACE ? reinterpret_cast<char*>(a.trace_reward) + tid * 16 : nullptr;
+  char* tr_done = TRACE ? reinterpret_cast<char*>(a.trace_done) + tid * 2 : nullptr;
 
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
@@ -459,10 +463,14 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
       bool d0, d1;
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0, r0, d0);
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1, r1, d1);
-      const int64_t off = (int64_t)t * a.n;
-      if (a.trace_obs) store2_stream<double2>(a.trace_obs + off, L, e0.s, e1.s);
-      if (a.trace_reward) store2_stream<double2>(a.trace_reward + off, L, r0, r1);
-      if (a.trace_done) store2_stream<uchar2>(a.trace_done + off, L, (uint8_t)d0, (uint8_t)d1);
+      // adjacent-pair layout and all three rows present (launch_rollout_p checks both): one 16-byte / 16-byte / 2-byte
+      // streaming store each through pointers that advance by one row per step
+      __stcs(reinterpret_cast<double2*>(tr_obs), make_double2(e0.s, e1.s));
+      __stcs(reinterpret_cast<double2*>(tr_rew), make_double2(r0, r1));
+      __stcs(reinterpret_cast<uchar2*>(tr_done), make_uchar2((uint8_t)d0, (uint8_t)d1));
+      tr_obs += row_f64;      // byte strides computed once: plain 64-bit adds, no multiply in the loop
+      tr_rew += row_f64;
+      tr_done += row_u8;
     } else {
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
       fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
@@ -663,7 +671,8 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   const bool tracing = a.trace_obs || a.trace_reward || a.trace_done || a.trace_action;
   // traces ride on the specialised kernel unless they include the action trace, the done-handling is freeze-on-done, the
   // policy is MSY, or the environments are laid out as a sweep
-  const bool fast_trace_ok = !a.trace_action && done_mode(a) != M_FREEZE && policy != FISHING_POLICY_MSY && a.noise_id_div <= 1;
+  const bool fast_trace_ok = !a.trace_action && a.trace_obs && a.trace_reward && a.trace_done && done_mode(a) != M_FREEZE &&
+                             policy != FISHING_POLICY_MSY && a.noise_id_div <= 1;
   const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
   constexpr int SWEEP_LV = 4;
