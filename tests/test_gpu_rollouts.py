@@ -80,3 +80,102 @@ def test_max_size_2pow24_shards_equal_whole_batch():
         parts.append(b.reduce_stats(o["ret"], o["done_step"], groups=256))
     assert torch.equal(tree_sum(parts), stats)
     assert float(stats[:, 0].sum()) > 0 and torch.isfinite(whole.state).all()
+
+
+def test_full_size_cfg4_v4_rollout_buffer_2pow22():
+    """BASELINE.json config 4 at its full size: fishing-v4, 2^22 environments, a 128-step rollout buffer filled by K1
+    (per-env K, r redrawn from the Philox stream at every auto-reset).  (i) the fused kernel with per-step rows == K1 x 128
+    bit for bit; (ii) two half shards with global ids == the whole batch; (iii) four blocks of 512 environments replayed
+    through the oracle over all 128 steps with the same actions and the engine's own exported reset draws."""
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.engine import EnvBatch
+
+    n, T = 1 << 22, 128
+    cfg = dict(r=0.3, K=1.0, sigma=0.0, sigma_p=0.1, x0=0.75, Tmax=100, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = torch.rand((T, n), dtype=torch.float64, device="cuda", generator=g) * 0.5 - 1.0
+    whole = EnvBatch(nat.V4, n, auto_reset=True, **cfg)
+    whole.reset()
+    K0, r0 = whole.K_env.clone(), whole.r_env.clone()
+    obs = torch.empty(T, n, dtype=torch.float64, device="cuda")
+    rew = torch.empty_like(obs)
+    done = torch.empty(T, n, dtype=torch.uint8, device="cuda")
+    whole.step_many(acts, obs, rew, done)
+    fused = EnvBatch(nat.V4, n, auto_reset=True, **cfg)
+    fused.reset()
+    out = fused.rollout(T, policy="actions", actions=acts, trace=True)
+    assert torch.equal(out["obs"], obs) and torch.equal(out["reward"], rew) and torch.equal(out["done"], done)
+    assert torch.equal(fused.K_env, whole.K_env) and torch.equal(fused.r_env, whole.r_env)
+    del out, fused
+    half, Th = n // 2, 32
+    for lo in (0, half):
+        part = EnvBatch(nat.V4, half, env_id0=lo, auto_reset=True, **cfg)
+        part.reset()
+        o2 = torch.empty(Th, half, dtype=torch.float64, device="cuda")
+        r2 = torch.empty_like(o2)
+        d2 = torch.empty(Th, half, dtype=torch.uint8, device="cuda")
+        part.step_many(acts[:Th, lo:lo + half].contiguous(), o2, r2, d2)
+        assert torch.equal(o2, obs[:Th, lo:lo + half]) and torch.equal(d2, done[:Th, lo:lo + half])
+        del part, o2, r2, d2
+    m = 512
+    for lo in (0, 1_000_000, 2_718_282 & ~1, n - m):
+        src = EnvBatch(nat.V4, m, env_id0=lo, **cfg)
+        rn = np.empty((T + 1, 2, m))
+        rn[0] = 0.0                                     # the explicit reset's draws are taken from the engine's K0, r0 below
+        rn[1:] = src.noise(T, stream=nat.STREAM_AUTORESET, step0=0).cpu().numpy()
+        exp = fo.rollout_vec("v4", T, m, r=r0[lo:lo + m].cpu().numpy(), K=K0[lo:lo + m].cpu().numpy(), sigma=0.0, x0=0.75,
+                             Tmax=100, policy="actions", actions=acts[:, lo:lo + m].cpu().numpy(), auto_reset=True,
+                             reset_noise=rn, K_mean=1.0, r_mean=0.3, sigma_p=0.1)
+        assert np.array_equal(obs[:, lo:lo + m].cpu().numpy(), exp["obs"]), lo
+        assert np.array_equal(rew[:, lo:lo + m].cpu().numpy(), exp["reward"]) and np.array_equal(done[:, lo:lo + m].cpu().numpy(), exp["done"])
+        assert np.array_equal(whole.K_env[lo:lo + m].cpu().numpy(), exp["K"]) and exp["done"].sum() > m
+
+
+def test_full_size_cfg5_sweep_1024_levels():
+    """BASELINE.json config 5 at one GPU's share of its full size: 1024 escapement levels x 2048 noise replicates x 1000
+    steps, common random numbers (warp-cooperative sweep kernel).  (i) two half shards of the replicate axis with global
+    ids == the whole batch, per environment and in the reduced statistics; (ii) two replicates x all 1024 levels replayed
+    through the oracle with the engine's exported noise; (iii) the sigma = 0 known answers of the reference at the three
+    levels that hit S = 0.25 / 0.5 / 0.75 exactly are reproduced by the levels of a 5-point grid (test above) -- here the
+    1024-level grid must give the same mean return for every replicate when sigma = 0."""
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.engine import EnvBatch
+
+    levels, reps, T = 1024, 2048, 1000
+    n = levels * reps
+    cfg = dict(r=0.3, K=1.0, sigma=0.1, x0=0.75, Tmax=1000, seed=0)
+    S_levels = torch.arange(levels, dtype=torch.float64, device="cuda") / (levels - 1)
+
+    def run(rep_lo, rep_n, **over):
+        c = dict(cfg, **over)
+        b = EnvBatch(nat.V1, rep_n * levels, env_id0=rep_lo * levels, **c)
+        b.reset()
+        out = b.rollout(T, policy="escapement", S_env=S_levels.repeat(rep_n).contiguous(), noise_id_div=levels, freeze_done=True)
+        return b, out
+
+    b, whole = run(0, reps)
+    stats = b.reduce_stats(whole["ret"], whole["done_step"], groups=levels)
+    parts = []
+    for lo in (0, reps // 2):
+        bp, o = run(lo, reps // 2)
+        sl = slice(lo * levels, (lo + reps // 2) * levels)
+        assert torch.equal(o["ret"], whole["ret"][sl]) and torch.equal(o["done_step"], whole["done_step"][sl])
+        parts.append(bp.reduce_stats(o["ret"], o["done_step"], groups=levels))
+    assert torch.equal(parts[0] + parts[1], stats)          # aligned power-of-two shards combine exactly
+    # oracle replay of replicates 6 and 7 (one Philox pair) at every level
+    z = EnvBatch(nat.V1, 2, env_id0=6, **cfg).noise(T, step0=0).cpu().numpy()          # [T, 2]: replicate 6 -> z0, 7 -> z1
+    for k in (6, 7):
+        e = fo.rollout_vec("v1", T, levels, r=0.3, K=1.0, sigma=0.1, x0=0.75, Tmax=1000, policy="escapement",
+                           S=S_levels.cpu().numpy(), noise=np.repeat(z[:, k - 6:k - 5], levels, axis=1), record=False)
+        got = whole["ret"][k * levels:(k + 1) * levels].cpu().numpy()
+        assert np.array_equal(got, e["ret"]), k
+        assert np.array_equal(whole["done_step"][k * levels:(k + 1) * levels].cpu().numpy(), e["done_step"])
+    # sigma = 0: every replicate of a level is the same deterministic trajectory
+    _, det = run(0, 4, sigma=0.0)
+    r4 = det["ret"].view(4, levels)
+    assert torch.equal(r4[0], r4[1]) and torch.equal(r4[0], r4[3])
+    assert float(r4[0].max()) > 75.0
