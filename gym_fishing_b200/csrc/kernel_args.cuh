@@ -21,6 +21,7 @@ struct StepArgs {
   double s_reset;     // x0 / K - 1 (x0 itself for v4), precomputed on the host with the same IEEE operations
   double K_mean, r_mean, sigma_p;
   double n_actions;
+  double rcp_n_actions;  // RN(1 / n_actions), computed on the host (div_count)
   int32_t Tmax;
   uint32_t flags;
   const void* __restrict__ action;
@@ -66,7 +67,7 @@ struct ResetArgs {
 struct RolloutArgs {
   int64_t n, env_id0, T;
   uint64_t step0, seed;
-  double r, K, sigma, C, s_reset, K_mean, r_mean, sigma_p, n_actions;
+  double r, K, sigma, C, s_reset, K_mean, r_mean, sigma_p, n_actions, rcp_n_actions;
   int32_t Tmax;
   uint32_t flags;
   int32_t discrete;      // fishing-v0: Discrete action space

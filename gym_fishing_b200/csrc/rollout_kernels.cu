@@ -142,13 +142,13 @@ __device__ __forceinline__ void load_action_pair(const RolloutArgs& a, const Lan
     case FISHING_ACT_I32: {
       const int2 v = load2_stream<int2>(reinterpret_cast<const int32_t*>(a.actions) + off, L);
       a0 = v.x; a1 = v.y;
-      q0 = quota_int<PM>(v.x, a.n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, K1);
+      q0 = quota_int<PM>(v.x, a.n_actions, a.rcp_n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, a.rcp_n_actions, K1);
       break;
     }
     default: {
       const longlong2 v = load2_stream<longlong2>(reinterpret_cast<const long long*>(a.actions) + off, L);
       a0 = (double)v.x; a1 = (double)v.y;
-      q0 = quota_int<PM>(v.x, a.n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, K1);
+      q0 = quota_int<PM>(v.x, a.n_actions, a.rcp_n_actions, K0); q1 = quota_int<PM>(v.y, a.n_actions, a.rcp_n_actions, K1);
       break;
     }
   }

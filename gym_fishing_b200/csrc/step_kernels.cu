@@ -23,7 +23,7 @@ template <int GROWTH, int PM, int ACT, bool DEFER_V4_DRAW = false, bool LEAN = f
 __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, double s, typename ActT<ACT>::type act,
                                              double z, bool noisy, int32_t years, double K, double r,
                                              int32_t model = 0) {
-  const double quota = quota_of<PM, ACT>(act, a.n_actions, K);
+  const double quota = quota_of<PM, ACT>(act, a.n_actions, a.rcp_n_actions, K);
   GrowthP gp_local;
   const GrowthP* gp = &a.gp;
   if (GROWTH == G_BEVERTON_HOLT && a.derive_on_device) {

@@ -680,6 +680,41 @@ def test_traced_fast_rollout_equals_generic_traces_and_single_steps(kind, cfg, a
             assert torch.equal(rew.view(torch.int64), f["reward"].view(torch.int64)) and torch.equal(done, f["done"])
 
 
+def test_discrete_quota_division_is_the_ieee_quotient():
+    """quota = (action / n_actions) * K (base_fishing_env.py:139-141) is computed with the reciprocal of n_actions and two
+    residual corrections (div_count, csrc/dynamics.cuh) instead of a hardware division; Markstein's theorem says the result
+    is the correctly rounded quotient.  Checked here against numpy's division for every n_actions in 1..2048 with every
+    action in -64..3263 (6.8 million pairs), and for random large values; both the lean kernel (reward) and the full one
+    (harvest output, which also shows negative quotas)."""
+    torch = _torch()
+    from gym_fishing_b200.engine import EnvBatch
+
+    acts_np = np.arange(-64, 3264, dtype=np.int64)
+    m = acts_np.size
+    acts = dev(acts_np)
+    state = torch.full((m,), 1e12, dtype=torch.float64, device="cuda")      # a stock no quota here exceeds
+    obs = torch.empty_like(state)
+    rew = torch.empty_like(state)
+    harv = torch.empty_like(state)
+    done = torch.empty(m, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(0)
+    counts = list(range(1, 2049)) + [int(v) for v in rng.integers(2049, 2 ** 31 - 1, size=64)] + [2 ** 31 - 1]
+    for n_actions in counts:
+        b = EnvBatch(0, m, r=0.3, K=1.0, sigma=0.0, x0=0.75, Tmax=10 ** 6, n_actions=n_actions)
+        want = acts_np.astype(np.float64) / np.float64(n_actions)
+        b.step(acts, state_in=state, out_obs=obs, out_reward=rew, out_done=done, out_harvest=harv)
+        got = harv.cpu().numpy()
+        assert np.array_equal(got, want), (n_actions, np.flatnonzero(got != want)[:5])
+        b.step(acts, state_in=state, out_obs=obs, out_reward=rew, out_done=done)          # lean kernel
+        assert np.array_equal(rew.cpu().numpy(), np.maximum(want, 0.0)), n_actions
+    big = rng.integers(-2 ** 62, 2 ** 62, size=m, dtype=np.int64)
+    state.fill_(1e300)
+    for n_actions in (1, 3, 7, 100, 12345, 2 ** 31 - 1):
+        b = EnvBatch(0, m, r=0.3, K=1.0, sigma=0.0, x0=0.75, Tmax=10 ** 6, n_actions=n_actions)
+        b.step(dev(big), state_in=state, out_obs=obs, out_reward=rew, out_done=done, out_harvest=harv)
+        assert np.array_equal(harv.cpu().numpy(), big.astype(np.float64) / np.float64(n_actions)), n_actions
+
+
 def test_special_values_bitwise_against_oracle():
     """NaN / inf / negative / signed-zero states, actions and noise through K1 (both paths) and K2: the comparisons
     removed from the kernels as provably redundant (max(x - h, 0), ...) must not change any bit on any input."""
