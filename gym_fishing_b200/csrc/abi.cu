@@ -244,6 +244,7 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
   a.n_actions = (double)p->n_actions;
   a.rcp_n_actions = 1.0 / (double)p->n_actions;
+  a.kd = make_kdiv(p->K, p->r);
   a.Tmax = p->Tmax; a.flags = p->flags & (FISHING_AUTO_RESET | FISHING_FREEZE_DONE);
   a.action = action; a.noise = noise; a.reset_noise = reset_noise;
   a.state_in = soa.state; a.years = soa.years; a.K_env = soa.K_env; a.r_env = soa.r_env;
@@ -355,6 +356,7 @@ int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const f
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
   a.n_actions = (double)p->n_actions;
   a.rcp_n_actions = 1.0 / (double)p->n_actions;
+  a.kd = make_kdiv(p->K, p->r);
   a.Tmax = p->Tmax; a.flags = p->flags;
   a.discrete = p->kind == FISHING_V0;
   a.action_dtype = r->action_dtype;

@@ -100,6 +100,33 @@ __device__ __forceinline__ double div_count(double a, double n, double rn) {
   q = __fma_rn(__fma_rn(-q, n, a), rn, q);
   return __fma_rn(__fma_rn(-q, n, a), rn, q);
 }
+// a / K for a carrying capacity K that is a constructor parameter (the same for every environment, but not 1): the host
+// supplies rK = RN(1 / K) and says whether K is an ordinary number (2^-500 <= K <= 2^500).  Then, for a zero or
+// with 2^-500 <= |a| < 2^501, nothing in the two-correction sequence can overflow or underflow and Markstein's theorem
+// applies as in div_count; everything else (NaN, infinities, extreme magnitudes, unusual K) takes the IEEE division.
+struct KDiv {
+  double rK;
+  int fast;
+  int odd;   // the uniform parameters are not (K > 0, r >= 0): see "sigma == 0" in grow()
+};
+inline KDiv make_kdiv(double K, double r) {
+  KDiv k;
+  k.fast = (K >= 0x1p-500 && K <= 0x1p500) ? 1 : 0;   // positive ordinary numbers only; false for NaN
+  k.rK = k.fast ? 1.0 / K : 0.0;
+  k.odd = (K > 0.0 && r >= 0.0) ? 0 : 1;
+  return k;
+}
+__device__ __forceinline__ double div_k(double a, double K, const KDiv& kd) {
+  const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;   // biased exponent of a
+  if (kd.fast && (e - 523u < 1001u || a == 0.0)) {
+    const double q0 = __dmul_rn(a, kd.rK);                            // for a zero: the zero of the right sign
+    double q = __fma_rn(__fma_rn(-q0, K, a), kd.rK, q0);
+    q = __fma_rn(__fma_rn(-q, K, a), kd.rK, q);
+    return (a == 0.0) ? q0 : q;
+  }
+  return div_z(a, K);
+}
+
 // (a / n_actions) * K for a Discrete action, base_fishing_env.py:139-141
 template <int PM>
 __device__ __forceinline__ double quota_int(long long a, double n_actions, double rcp_n_actions, double K) {
@@ -110,28 +137,34 @@ __device__ __forceinline__ double quota_int(long long a, double n_actions, doubl
 
 // get_action, base_fishing_env.py:149-156
 template <int PM>
-__device__ __forceinline__ double action_cts(double q, double K) {
-  return __dsub_rn(PM == P_KONE ? q : div_z(q, K), 1.0);
+__device__ __forceinline__ double action_cts(double q, double K, const KDiv& kd = KDiv()) {
+  return __dsub_rn(PM == P_KONE ? q : (PM == P_UNIFORM ? div_k(q, K, kd) : div_z(q, K)), 1.0);
 }
 template <int PM>
-__device__ __forceinline__ double action_discrete(double q, double n_actions, double K) {
+__device__ __forceinline__ double action_discrete(double q, double n_actions, double K, const KDiv& kd = KDiv()) {
   const double t = __dmul_rn(q, n_actions);
-  return rint(PM == P_KONE ? t : div_z(t, K));  // Python round(): half to even, not range checked
+  return rint(PM == P_KONE ? t : (PM == P_UNIFORM ? div_k(t, K, kd) : div_z(t, K)));  // Python round(): half to even
 }
 
 // population_draw: base_fishing_env.py:121-133 (logistic) / fishing_tipping_env.py:24-35 (tipping point)
 template <int GROWTH, int PM>
-__device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy) {
-  const double frac = PM == P_KONE ? x1 : div_z(x1, K);
+__device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy,
+                                       const KDiv& kd = KDiv()) {
+  const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, K, kd) : div_z(x1, K));
   const double room = __dsub_rn(1.0, frac);
   if (GROWTH == LOGISTIC) {
     double t = __dadd_rn(x1, __dmul_rn(__dmul_rn(r, x1), room));
-    // sigma == 0 adds +-0.0, which cannot change the clipped result (see DESIGN.md "noise when sigma = 0")
+    // sigma == 0: the reference still adds (x1 * 0) * z.  For a finite stock that is +-0.0 and cannot change the clipped
+    // result, so no draw is made.  For an infinite stock it is NaN -- which the growth term already is (inf - inf) whenever
+    // K > 0 and r >= 0; only for other parameter signs (or caller-supplied per-env K, r) does the term have to be added
+    // (DESIGN.md "noise when sigma = 0").
     if (noisy) t = __dadd_rn(t, __dmul_rn(__dmul_rn(x1, sigma), z));
+    else if (PM == P_PERENV || kd.odd) t = __dadd_rn(t, __dmul_rn(x1, 0.0));
     return np_max0(t);
   } else {
     double e = __dmul_rn(__dmul_rn(r, room), __dsub_rn(x1, C));
     if (noisy) e = __dadd_rn(e, __dmul_rn(__dmul_rn(x1, sigma), z));
+    else if (PM == P_PERENV || kd.odd) e = __dadd_rn(e, __dmul_rn(x1, 0.0));
     return np_max0(__dmul_rn(x1, exp(e)));
   }
 }
@@ -220,7 +253,7 @@ struct StepOut {
 template <int GROWTH, int PM>
 __device__ __forceinline__ StepOut step_core(double s, double quota, double z, double r, double K, double C,
                                              double sigma, bool noisy, const GrowthP* gp = nullptr,
-                                             const ModelTable* tab = nullptr, int model = 0) {
+                                             const ModelTable* tab = nullptr, int model = 0, const KDiv& kd = KDiv()) {
   // gp / tab are only dereferenced by the log-normal growth family (fishing-v5..v11)
   double x = __dadd_rn(s, 1.0);                     // get_fish_population :158-160
   if (PM != P_KONE) x = __dmul_rn(x, K);
@@ -229,11 +262,12 @@ __device__ __forceinline__ StepOut step_core(double s, double quota, double z, d
   // positive number or NaN for every input, and Python's max(v, 0.0) returns v in all three cases
   const double x1 = __dsub_rn(x, h);
   double x2;
-  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy);
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy, kd);
   else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);
   StepOut o;
   // get_state :162-164 (the log-normal family always takes the general-K path, with K = 1 by default: div_u)
-  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) o.s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, K), 1.0);
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING)
+    o.s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, K, kd) : div_z(x2, K)), 1.0);
   else o.s2 = __dsub_rn(div_u(x2, K), 1.0);
   o.reward = py_max(h, 0.0);                        // :74
   o.dead = x2 <= 0.0;                               // :78

@@ -22,6 +22,7 @@ struct StepArgs {
   double K_mean, r_mean, sigma_p;
   double n_actions;
   double rcp_n_actions;  // RN(1 / n_actions), computed on the host (div_count)
+  KDiv kd;               // reciprocal of the uniform K (div_k)
   int32_t Tmax;
   uint32_t flags;
   const void* __restrict__ action;
@@ -68,6 +69,7 @@ struct RolloutArgs {
   int64_t n, env_id0, T;
   uint64_t step0, seed;
   double r, K, sigma, C, s_reset, K_mean, r_mean, sigma_p, n_actions, rcp_n_actions;
+  KDiv kd;               // reciprocal of the uniform K (div_k)
   int32_t Tmax;
   uint32_t flags;
   int32_t discrete;      // fishing-v0: Discrete action space

@@ -98,12 +98,12 @@ __device__ __forceinline__ double policy_quota_escapement(const RolloutArgs& a, 
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
   const double q = py_max(__dsub_rn(x, e.S), 0.0);
   if (a.discrete) {
-    const double act = action_discrete<PM>(q, a.n_actions, e.K);
+    const double act = action_discrete<PM>(q, a.n_actions, e.K, a.kd);
     action_out = act;
     const double t = div_z(act, a.n_actions);
     return PM == P_KONE ? t : __dmul_rn(t, e.K);
   }
-  const double act = action_cts<PM>(q, e.K);
+  const double act = action_cts<PM>(q, e.K, a.kd);
   action_out = act;
   return quota_f64<PM>(act, e.K);
 }
@@ -112,12 +112,12 @@ template <int PM>
 __device__ __forceinline__ double policy_quota_msy(const RolloutArgs& a, double K, double& action_out) {
   // msy.predict, policies.py:16-19: action = get_action(msy) every step; constant per environment
   if (a.discrete) {
-    const double act = action_discrete<PM>(a.msy_q, a.n_actions, K);
+    const double act = action_discrete<PM>(a.msy_q, a.n_actions, K, a.kd);
     action_out = act;
     const double t = div_z(act, a.n_actions);
     return PM == P_KONE ? t : __dmul_rn(t, K);
   }
-  const double act = action_cts<PM>(a.msy_q, K);
+  const double act = action_cts<PM>(a.msy_q, K, a.kd);
   action_out = act;
   return quota_f64<PM>(act, K);
 }
@@ -158,7 +158,7 @@ template <int GROWTH, int PM>
 __device__ __forceinline__ void env_advance(const RolloutArgs& a, const GrowthP& gp, EnvReg& e, double quota, double z,
                                             bool noisy, int64_t t, uint64_t gid, double& obs, double& reward,
                                             uint8_t& done) {
-  const StepOut o = step_core<GROWTH, PM>(e.s, quota, z, e.r, e.K, a.C, a.sigma, noisy, &gp, &a.tab, e.model);
+  const StepOut o = step_core<GROWTH, PM>(e.s, quota, z, e.r, e.K, a.C, a.sigma, noisy, &gp, &a.tab, e.model, a.kd);
   e.years += 1;
   done = (e.years > a.Tmax) || o.dead;
   reward = o.reward;
@@ -326,7 +326,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   double quota;
   if (POLICY == FISHING_POLICY_ESCAPEMENT) {
     const double q = py_max(__dsub_rn(x, e.S), 0.0);            // policies.py:29
-    double act = action_cts<PM>(q, e.K);                         // get_action, base_fishing_env.py:156
+    double act = action_cts<PM>(q, e.K, a.kd);                   // get_action, base_fishing_env.py:156
     act = (act > 1.0) ? 1.0 : act;                               // np.clip: the lower bound cannot fire (act >= -1)
     quota = __dadd_rn(act, 1.0);
     if (PM != P_KONE) quota = __dmul_rn(quota, e.K);
@@ -337,20 +337,22 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
   const double h = py_min(x, quota);
   const double x1 = __dsub_rn(x, h);                             // == max(x - h, 0.0)
-  const double frac = PM == P_KONE ? x1 : div_z(x1, e.K);
+  const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, e.K, a.kd) : div_z(x1, e.K));
   const double room = __dsub_rn(1.0, frac);
   double g;
   if (GROWTH == LOGISTIC) {
     g = __dadd_rn(x1, __dmul_rn(__dmul_rn(e.r, x1), room));
     if (NOISY) g = __dadd_rn(g, __dmul_rn(__dmul_rn(x1, a.sigma), z));
+    else if (PM == P_PERENV) g = __dadd_rn(g, __dmul_rn(x1, 0.0));   // see grow(): sigma == 0 (odd uniform parameters: generic kernel)
   } else {
     double ex = __dmul_rn(__dmul_rn(e.r, room), __dsub_rn(x1, a.C));
     if (NOISY) ex = __dadd_rn(ex, __dmul_rn(__dmul_rn(x1, a.sigma), z));
+    else if (PM == P_PERENV) ex = __dadd_rn(ex, __dmul_rn(x1, 0.0));
     g = __dmul_rn(x1, exp(ex));
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
   const double x2 = alive ? g : 0.0;
-  const double s2 = __dsub_rn(PM == P_KONE ? x2 : div_z(x2, e.K), 1.0);
+  const double s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, e.K, a.kd) : div_z(x2, e.K)), 1.0);
   const double reward = py_max(h, 0.0);
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;
@@ -673,7 +675,9 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
   // policy is MSY, or the environments are laid out as a sweep
   const bool fast_trace_ok = !a.trace_action && a.trace_obs && a.trace_reward && a.trace_done && done_mode(a) != M_FREEZE &&
                              policy != FISHING_POLICY_MSY && a.noise_id_div <= 1;
-  const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && a.T <= 0x7fffffffLL &&
+  // noise-free runs with uniform parameters outside (K > 0, r >= 0) need the explicit x * 0 term of grow(): generic kernel
+  const bool odd_noise_free = a.kd.odd && a.sigma == 0.0;
+  const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && !odd_noise_free && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
   constexpr int SWEEP_LV = 4;
   const bool sweep = fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && sweep_mode() != 1;

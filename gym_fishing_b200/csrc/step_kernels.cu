@@ -31,7 +31,7 @@ __device__ __forceinline__ EnvResult advance(const StepArgs& a, int64_t i, doubl
     growth_derive(gp_local, FISHING_FN_BEVERTON_HOLT);
     gp = &gp_local;
   }
-  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy, gp, &a.tab, model);
+  const StepOut o = step_core<GROWTH, PM>(s, quota, z, r, K, a.C, a.sigma, noisy, gp, &a.tab, model, a.kd);
   EnvResult e;
   e.model = model;
   e.years = years + 1;                                   // base_fishing_env.py:75

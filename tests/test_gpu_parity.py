@@ -715,6 +715,52 @@ def test_discrete_quota_division_is_the_ieee_quotient():
         assert np.array_equal(harv.cpu().numpy(), big.astype(np.float64) / np.float64(n_actions)), n_actions
 
 
+@pytest.mark.parametrize("K", [2.5, 0.3, -1.5, 2.0 ** -500, 2.0 ** 500, 2.0 ** -501, 2.0 ** 501, 1e-160, 7e150, float("inf")])
+def test_uniform_K_division_is_the_ieee_quotient(K):
+    """x / K for a uniform K != 1 goes through the host's reciprocal and two residual corrections when K and x are ordinary
+    numbers (div_k, csrc/dynamics.cuh) and through the IEEE division otherwise.  One lock-step and a 3-step fused rollout
+    of fishing-v1 / v2 with states whose magnitudes straddle every guard (zeros, denormals, 2^-502..2^-498, 2^498..2^502,
+    infinities, NaN, ordinary values) must match the oracle (numpy's true division) bit for bit."""
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    mags = np.concatenate([2.0 ** rng.uniform(-504, -496, 2000), 2.0 ** rng.uniform(496, 504, 2000), rng.uniform(0, 3, 4000),
+                           2.0 ** rng.uniform(-1074, -1000, 500), 2.0 ** rng.uniform(-40, 40, 1500),
+                           [0.0, np.inf, np.nan, 5e-324, 1.7e308, 1.0, 2.0 ** -500, 2.0 ** 501]])
+    x = mags * np.abs(K) if np.isfinite(K) else mags
+    with np.errstate(all="ignore"):
+        s0 = x / K - 1.0                               # states whose stock (s + 1) * K lands on the magnitudes above
+        s0 = np.concatenate([s0, mags - 1.0, -mags - 1.0])
+    n = s0.size + (s0.size & 1)
+    s0 = np.resize(s0, n)
+    acts = rng.uniform(-1.0, -0.2, size=(3, n))
+    for kind in ("v1", "v2"):
+        cfg = dict(r=0.3, K=K, sigma=0.0, C=0.5, x0=0.75, Tmax=5)
+        b = make_batch(kind, n, **cfg)
+        b.reset()
+        b.state.copy_(dev(s0))
+        obs = torch.empty(3, n, dtype=torch.float64, device="cuda")
+        rew = torch.empty_like(obs)
+        done = torch.empty(3, n, dtype=torch.uint8, device="cuda")
+        for t in range(3):
+            b.step(dev(acts[t]), out_obs=obs[t], out_reward=rew[t], out_done=done[t])
+        with np.errstate(all="ignore"):
+            exp = fo.rollout_vec(kind, 3, n, r=0.3, K=K, sigma=0.0, C=0.5, x0=0.75, Tmax=5, policy="actions", actions=acts, s0=s0)
+        if kind == "v1":
+            assert np.array_equal(obs.cpu().numpy(), exp["obs"], equal_nan=True), K
+            assert np.array_equal(rew.cpu().numpy(), exp["reward"], equal_nan=True)
+            assert np.array_equal(done.cpu().numpy(), exp["done"])
+        else:   # one exp evaluation: after that an ulp of difference is amplified without bound on these explosive states
+            same(obs[0].cpu().numpy(), exp["obs"][0], kind, "obs", max(abs(K), 1.0) if np.isfinite(K) else 1.0)
+            assert np.array_equal(done[0].cpu().numpy(), exp["done"][0])
+        b2 = make_batch(kind, n, **cfg)
+        b2.reset()
+        b2.state.copy_(dev(s0))
+        out = b2.rollout(3, policy="actions", actions=dev(acts))
+        assert torch.equal(b2.state.view(torch.int64), obs[2].view(torch.int64)), (kind, K)
+        if kind == "v1":
+            assert np.array_equal(out["ret"].cpu().numpy(), exp["ret"], equal_nan=True)
+
+
 def test_special_values_bitwise_against_oracle():
     """NaN / inf / negative / signed-zero states, actions and noise through K1 (both paths) and K2: the comparisons
     removed from the kernels as provably redundant (max(x - h, 0), ...) must not change any bit on any input."""
