@@ -8,7 +8,8 @@ def run(kind, acts, **kw):
     obs = torch.empty(T, n, dtype=torch.float64, device=dev); rew = torch.empty_like(obs)
     done = torch.empty(T, n, dtype=torch.uint8, device=dev)
     b = EnvBatch(kind, n, device=dev, auto_reset=True, Tmax=100, **kw); b.reset()
-    b.step_many(acts, obs, rew, done); torch.cuda.synchronize()
+    for _ in range(3): b.step_many(acts, obs, rew, done)
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3): b.step_many(acts, obs, rew, done)
