@@ -16,6 +16,7 @@ All dynamics run in the sm_100a kernels of libfishing_b200.so; there is no CPU p
 from __future__ import annotations
 
 import ctypes as ct
+import os
 
 import numpy as np
 
@@ -105,6 +106,9 @@ def normalise_kwargs(kind, kw):
             out[k] = kw[k]
     out["x0"] = kw.get("init_state", 0.75)
     return out
+
+
+_ZC_MAX = int(os.environ.get("FISHING_VEC_ZC_MAX", 65536))   # keep in step with zero_copy_max_envs() in csrc/abi.cu
 
 
 class LazyInfos:
@@ -359,6 +363,10 @@ class FishingVecEnv:
             done = d8.array.view(np.bool_)
             return (o32.array.reshape(n, 1), r32.array, done, LazyInfos(done, _LazyTerminal(self) if self.auto_reset else None))
         self._h_obs, self._h_reward, self._h_done = self._h_sets[self._h_flip]
+        if n <= _ZC_MAX:   # small batch: stage the actions in page-locked memory so that the library can take its one-launch route
+            staged = self._h_act.array.view(a.dtype)[:n]
+            np.copyto(staged, a)
+            a = staged
         rc = nat.lib().fishing_vec_step(self._handle, a.ctypes.data, adt, None, self._h_obs.array.ctypes.data,
                                         self._h_reward.array.ctypes.data, self._h_done.array.ctypes.data, None)
         nat.check(rc, "fishing_vec_step")

@@ -1,7 +1,7 @@
 import sys, time, torch
 sys.path.insert(0, "/root/repo")
 import gym_fishing_b200 as gf
-for n in (1024, 65536):
+for n in (1024, 16384, 65536, 262144, 1048576):
     for io in ("torch", "numpy"):
         v = gf.FishingVecEnv("fishing-v1", num_envs=n, device="cuda", io=io, seed=0, sigma=0.01)
         obs = v.reset()
