@@ -222,6 +222,7 @@ class FishingVecEnv:
             self._reward2 = [torch.empty(self.num_envs, dtype=torch.float64, device=self.device) for _ in range(2)]
             self._done2 = [torch.empty(self.num_envs, dtype=torch.uint8, device=self.device) for _ in range(2)]
             self._flip = 0
+            self._act_dtype = torch.int64 if self.kind == nat.V0 else torch.float64
             self.terminal_obs = torch.full((self.num_envs,), float("nan"), dtype=torch.float64, device=self.device)
             if self.monitor:
                 self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
@@ -295,6 +296,9 @@ class FishingVecEnv:
 
     def _coerce_torch_actions(self, actions):
         torch = self.batch.torch
+        if (torch.is_tensor(actions) and actions.dtype == self._act_dtype and actions.device == self.device
+                and actions.is_contiguous() and actions.numel() == self.num_envs):
+            return actions.view(self.num_envs)      # the common case: nothing to convert
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
         if actions.device != self.device:
@@ -312,8 +316,8 @@ class FishingVecEnv:
         a = self._coerce_torch_actions(actions)
         self._flip ^= 1
         k = self._flip
-        obs, rew, done = b.step(a, out_obs=self._obs2[k], out_reward=self._reward2[k], out_done=self._done2[k],
-                                out_terminal=self.terminal_obs if self.auto_reset else None)
+        obs, rew, done = b.step_trusted(a, self._obs2[k], self._reward2[k], self._done2[k],
+                                        self.terminal_obs if self.auto_reset else None)
         done_b = done.view(b.torch.bool)
         episode = None
         if self.monitor:
