@@ -464,3 +464,17 @@ def test_user_action_policy_reads_a_quota_from_stdin(monkeypatch):
         assert "fish population: 0.75" in prompts[0] and state is obs
         assert action == expect
         env.step(action)
+
+
+def test_dqn_example_learns_on_the_discrete_env():
+    """examples/dqn_torch.py, the counterpart of the reference's tests/test-DQN.py: epsilon-greedy DQN on the batched
+    fishing-v0 (int64 actions, terminal observations for the bootstrap) must leave the random policy well behind."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("dqn_torch", os.path.join(root, "examples", "dqn_torch.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rets = mod.main(["--envs", "4096", "--iters", "300"])
+    assert len(rets) > 20 and rets[0] < 1.5 and max(rets[-5:]) > 2.5
