@@ -93,6 +93,13 @@ template <int GROWTH, int PM, int ACT, int BS = 128, bool LEAN = false>
 __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 : 0) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
+  // fishing-v4 reset jobs of the whole block (see the end of the kernel)
+  __shared__ unsigned s_count, s_arrived;
+  __shared__ uint16_t s_job[2 * BS];
+  if (PM == P_PERENV) {
+    if (threadIdx.x == 0) { s_count = 0; s_arrived = 0; }
+    __syncthreads();
+  }
   const int npairs = (int)(a.n >> 1);
   const int j = (int)(blockIdx.x * (unsigned)BS + threadIdx.x);
   const bool live = j < npairs;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
     }
   }
   if (a.flags & STEP_FLAG_PDL) pdl_wait();
-  // the fishing-v4 kernel keeps idle lanes of the last warp alive: its reset draws are shared out over the warp below
+  // the fishing-v4 kernel keeps idle lanes alive: every warp of the block has to sign off at the end (reset job list)
   if (!live && PM != P_PERENV) return;
 
   // ---- phase B: state written by the previous launch
@@ -149,62 +156,62 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
     e0 = advance<GROWTH, PM, ACT, true, LEAN>(a, i0, s.x, act.x, z.x, noisy, yr.x, Kv.x, rv.x, mdl.x);
     e1 = advance<GROWTH, PM, ACT, true, LEAN>(a, i0 + 1, s.y, act.y, z.y, noisy, yr.y, Kv.y, rv.y, mdl.y);
   }
-  if (PM == P_PERENV) {
-    if ((a.flags & FISHING_AUTO_RESET) && (LEAN || !a.reset_noise)) {
-      // Warp-cooperative parameter redraw.  A reset needs a Philox block + Box-Muller (~200 instructions); left inside
-      // advance() every warp would execute that path twice per step (once per environment slot) as soon as ANY lane
-      // resets.  Instead the resets of the warp's 64 environments are numbered with ballots, lane k draws for reset
-      // number k (all in one pass unless more than 32 environments of the warp reset at once), and the owners fetch
-      // their (K, r) with shuffles.  Same draws as the per-lane path: ctr = (global env id, step), stream AUTORESET.
-      // Job k -> owning environment slot goes through a per-warp table in shared memory (one byte store per reset, one
-      // byte load per job): the find-nth-set-bit alternative (__fns) is a ~100-instruction software loop.
-      __shared__ uint8_t s_owner[BS / 32][64];
-      const unsigned full = 0xffffffffu;
-      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      const unsigned m0 = __ballot_sync(full, e0.reset_fired), m1 = __ballot_sync(full, e1.reset_fired);
-      const int n0 = __popc(m0), total = n0 + __popc(m1);
-      const unsigned below = (1u << lane) - 1u;
-      const int job0 = __popc(m0 & below), job1 = n0 + __popc(m1 & below);
-      if (total > 0) {
-        if (e0.reset_fired) s_owner[warp][job0] = (uint8_t)(2 * lane);
-        if (e1.reset_fired) s_owner[warp][job1] = (uint8_t)(2 * lane + 1);
-        __syncwarp();
+  // the (K, r) redraw of environments that reset in this step is done for the whole block at the end of the kernel
+  const bool deferred = PM == P_PERENV && (a.flags & FISHING_AUTO_RESET) && (LEAN || !a.reset_noise);
+  if (live) {
+    reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
+    if (!LEAN && a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
+    st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
+    st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
+    reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
+    if (!LEAN && a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
+    if (!LEAN && a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
+    if (e0.reset_fired | e1.reset_fired) {
+      if (!LEAN && a.out_terminal) {
+        if (e0.reset_fired) a.out_terminal[i0] = e0.terminal;
+        if (e1.reset_fired) a.out_terminal[i0 + 1] = e1.terminal;
       }
-      for (int base = 0; base < total; base += 32) {
-        const int k = base + lane;
-        double Kn = 0.0, rn = 0.0;
-        if (k < total) {
-          const int slot = s_owner[warp][k];   // 2 * owner lane + (second environment of the pair)
-          const uint64_t gid = (uint64_t)(a.env_id0 + 2 * ((int64_t)j - lane) + slot);
-          const Normal2 d = normal_pair_keys(a.keys, gid, a.step_idx, FISHING_STREAM_AUTORESET);
-          Kn = v4_param(a.K_mean, a.sigma_p, d.z0);
-          rn = v4_param(a.r_mean, a.sigma_p, d.z1);
-        }
-        const double K0 = __shfl_sync(full, Kn, (job0 - base) & 31), r0 = __shfl_sync(full, rn, (job0 - base) & 31);
-        const double K1 = __shfl_sync(full, Kn, (job1 - base) & 31), r1 = __shfl_sync(full, rn, (job1 - base) & 31);
-        if (e0.reset_fired && job0 >= base && job0 < base + 32) { e0.K = K0; e0.r = r0; }
-        if (e1.reset_fired && job1 >= base && job1 < base + 32) { e1.K = K1; e1.r = r1; }
+      if (PM == P_PERENV && !deferred) {
+        reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
+        reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
       }
+      if (GROWTH == G_MODEL) reinterpret_cast<int2*>(a.model)[j] = make_int2(e0.model, e1.model);
     }
-    if (!live) return;
   }
-  reinterpret_cast<double2*>(a.out_obs)[j] = make_double2(e0.obs, e1.obs);
-  if (!LEAN && a.out_obs2) st_stream(reinterpret_cast<double2*>(a.out_obs2) + j, make_double2(e0.obs, e1.obs));
-  st_stream(reinterpret_cast<double2*>(a.out_reward) + j, make_double2(e0.reward, e1.reward));
-  st_stream(reinterpret_cast<uchar2*>(a.out_done) + j, make_uchar2(e0.done, e1.done));
-  reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
-  if (!LEAN && a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
-  if (!LEAN && a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
-  if (e0.reset_fired | e1.reset_fired) {
-    if (!LEAN && a.out_terminal) {
-      if (e0.reset_fired) a.out_terminal[i0] = e0.terminal;
-      if (e1.reset_fired) a.out_terminal[i0 + 1] = e1.terminal;
+  if (deferred) {
+    // Block-wide parameter redraw without a barrier.  A reset needs a Philox block + Box-Muller (~200 instructions), and
+    // with 64 environments per warp nearly every warp has at least one reset per step, so a per-warp pass runs at ~20 %
+    // lane utilisation.  Instead every warp appends its resets to a job list in shared memory and signs off; the warp that
+    // signs off LAST draws for the whole block (ceil(jobs / 32) passes instead of one per warp) and writes the new K and r
+    // straight to the state arrays -- nobody waits for anybody, the other warps have already retired.  Same draws as the
+    // per-lane path: ctr = (global env id, step), stream AUTORESET.
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned m0 = __ballot_sync(full, e0.reset_fired), m1 = __ballot_sync(full, e1.reset_fired);
+    const int n0 = __popc(m0), mine = n0 + __popc(m1);
+    if (mine > 0) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, (unsigned)mine);
+      base = __shfl_sync(full, base, 0);
+      const unsigned below = (1u << lane) - 1u;
+      if (e0.reset_fired) s_job[base + __popc(m0 & below)] = (uint16_t)(2 * threadIdx.x);
+      if (e1.reset_fired) s_job[base + n0 + __popc(m1 & below)] = (uint16_t)(2 * threadIdx.x + 1);
     }
-    if (PM == P_PERENV) {
-      reinterpret_cast<double2*>(a.K_env)[j] = make_double2(e0.K, e1.K);
-      reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
+    __threadfence_block();
+    unsigned arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&s_arrived, 1u);
+    arrived = __shfl_sync(full, arrived, 0);
+    if (arrived == BS / 32 - 1) {
+      __threadfence_block();
+      const int total = (int)*reinterpret_cast<volatile unsigned*>(&s_count);
+      const int64_t block0 = 2 * (int64_t)(blockIdx.x * (unsigned)BS);
+      for (int k = lane; k < total; k += 32) {
+        const int64_t i = block0 + reinterpret_cast<volatile uint16_t*>(s_job)[k];
+        const Normal2 d = normal_pair_keys(a.keys, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET);
+        a.K_env[i] = v4_param(a.K_mean, a.sigma_p, d.z0);
+        a.r_env[i] = v4_param(a.r_mean, a.sigma_p, d.z1);
+      }
     }
-    if (GROWTH == G_MODEL) reinterpret_cast<int2*>(a.model)[j] = make_int2(e0.model, e1.model);
   }
 }
 
