@@ -236,3 +236,33 @@ def test_hot_kernels_keep_their_register_budget():
     assert fast and all(u["REG"] <= 64 and u["STACK"] == 0 for u in fast), fast
     sweep = [u for n, u in usage.items() if "rollout_sweep_kernelILi0ELi0E" in n]
     assert sweep and all(u["REG"] <= 128 and u["STACK"] == 0 for u in sweep), sweep
+
+
+def test_two_correction_quotient_is_correctly_rounded_in_exact_arithmetic():
+    """div_count / div_k (csrc/dynamics.cuh) replace a / b by q0 = RN(a * y), then twice q = RN(q + RN(a - q * b) * y) with
+    y = RN(1 / b), each inner a - q * b and q + r * y being ONE fused operation.  The same sequence evaluated here with exact
+    rationals (Fraction -> float conversion rounds to nearest even, i.e. it is the fused operation) must give the IEEE
+    quotient for random operands, for divisors whose significand is nearly all ones or all zeros, and for numerators next
+    to powers of two -- the corners where a merely faithful quotient would differ."""
+    from fractions import Fraction
+
+    def fma(x, y, z):   # RN(x * y + z), exactly
+        return float(Fraction(x) * Fraction(y) + Fraction(z))
+
+    def div2(a, b):
+        y = 1.0 / b
+        q = a * y
+        q = fma(fma(-q, b, a), y, q)
+        return fma(fma(-q, b, a), y, q)
+
+    rng = np.random.default_rng(7)
+    n = 60000
+    a = np.concatenate([rng.uniform(0, 4, n), 2.0 ** rng.uniform(-40, 40, n), rng.integers(-64, 4000, n).astype(np.float64)])
+    b = np.concatenate([rng.uniform(0.25, 4, n), 2.0 ** rng.uniform(-20, 20, n), rng.integers(1, 5000, n).astype(np.float64)])
+    ones = np.nextafter(2.0 ** rng.integers(-3, 4, 4000).astype(np.float64), 0.0)          # 1.111...1 x 2^k
+    zeros = np.nextafter(2.0 ** rng.integers(-3, 4, 4000).astype(np.float64), np.inf)      # 1.000...1 x 2^k
+    a = np.concatenate([a, rng.uniform(0, 4, 8000), np.nextafter(2.0 ** rng.integers(-3, 4, 4000).astype(np.float64), 0.0),
+                        rng.uniform(0, 4, 4000)])
+    b = np.concatenate([b, ones, zeros, ones, ones[::-1]])
+    bad = [(x, d) for x, d in zip(a.tolist(), b.tolist()) if div2(x, d) != x / d]
+    assert not bad, bad[:5]
