@@ -9,7 +9,7 @@ is ONE pass of T=1000 lock-steps over the batch = T * n env-steps, i.e. T launch
 126 MB L2, so consecutive bench steps cannot be served from cache.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
-    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port), all cores
+    python bench.py --impl reference [...]                         # the unmodified reference's step() loop, all host cores
 
 Multi-GPU: one process per GPU under torchrun; environments are independent ("replicas only" for the VecEnv
 workload), every rank steps its own 2^20-env shard of the global id range, the time is the max
@@ -137,16 +137,7 @@ def _port_worker(args):
 
 
 def cpu_port_throughput(steps_per_proc, procs):
-    if procs == 1:
-        dt = _port_worker((steps_per_proc, 0))
-        return steps_per_proc / dt
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        pool.map(_port_worker, [(1000, i) for i in range(procs)])  # warm the workers (imports)
-        t0 = time.perf_counter()
-        pool.map(_port_worker, [(steps_per_proc, i) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    return steps_per_proc * procs / wall
+    return cpu_loop_throughput(_port_worker, steps_per_proc, procs)
 
 
 def cpu_vectorised_throughput(n=1 << 20, T=8):
@@ -195,28 +186,77 @@ def cpu_c_port_throughput(n=1 << 20, T=16):
     return best
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "gym_fishing"))
+
+
+def _ref_worker(args):
+    """`steps` env.step calls of the UNMODIFIED reference (baseline/_ref/gym_fishing, installed by baseline/install_ref.py)
+    under the gym / matplotlib stand-ins of oracle/refstub (neither package is in the image): the loop a user of
+    boettiger-lab/gym_fishing runs -- gym.make("fishing-v1", ...), env.step(action), env.reset() on done."""
+    steps, seed = args
+    for p in (os.path.join(ROOT, "oracle", "refstub"), REF_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gym
+    import gym_fishing  # noqa: F401  (registers the ids)
+    import numpy as np
+
+    np.random.seed(seed)
+    env = gym.make("fishing-v1", r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
+    acts = np.random.uniform(-1, 1, size=(1024, 1))
+    env.reset()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, _, done, _ = env.step(acts[i & 1023])
+        if done:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+def cpu_loop_throughput(worker, steps_per_proc, procs):
+    if procs == 1:
+        return steps_per_proc / worker((steps_per_proc, 0))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(worker, [(1000, i) for i in range(procs)])  # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(worker, [(steps_per_proc, i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    return steps_per_proc * procs / wall
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
-    to the GPU box, so this times the oracle's reference-shaped scalar port (same numpy-scalar operations per step,
-    validated bit-for-bit against the reference in tests/test_oracle_golden.py) on every host core."""
+    """--impl reference: the reference's own CPU implementation of the path, on every host core.  When baseline/_ref holds
+    the unmodified reference package (baseline/install_ref.py; it travels with the tree) THAT is what runs
+    (cpu_baseline.kind = "reference"); otherwise the oracle's reference-shaped scalar port (kind = "port": the same
+    numpy-scalar operations per step, validated bit for bit against the reference in tests/test_oracle_golden.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     per_proc = args.ref_steps_per_core
+    have_ref = reference_available() and not args.ref_port
+    worker = _ref_worker if have_ref else _port_worker
     vals = []
     for _ in range(args.warmup):
-        cpu_port_throughput(max(1000, per_proc // 10), cores)
+        cpu_loop_throughput(worker, max(1000, per_proc // 10), cores)
     for _ in range(args.steps):
-        vals.append(cpu_port_throughput(per_proc, cores))
+        vals.append(cpu_loop_throughput(worker, per_proc, cores))
     v = sum(vals) / len(vals)
-    sample = f"{per_proc} env.step calls per process x {cores} processes per bench step, fishing-v1 sigma=0.01, auto-reset on done"
+    what = ("the unmodified reference (baseline/_ref/gym_fishing, gym.make('fishing-v1') under the oracle/refstub gym stand-in)"
+            if have_ref else "oracle.ScalarPortEnv (" + ("--ref-port" if args.ref_port else "baseline/_ref is absent on this machine") + ")")
+    sample = (f"{per_proc} env.step calls per process x {cores} processes per bench step of {what}, fishing-v1 sigma=0.01, "
+              "reset() on done")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * per_proc * cores / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -374,6 +414,61 @@ def run_gpu(args):
     del obs, rew, done, b3
     torch.cuda.empty_cache()
 
+    # ---- BASELINE.json configs 3 and 5 at FULL size, sharded over the ranks of this run (strong scaling: the global problem is
+    # the same for every N, so the statistics -- and the checksums below -- must be identical for N = 1, 2, 4, 8).  Each timed
+    # call contains everything: reset (K3), the fused rollout (K2), the per-GPU reduction (K4) and the ONE collective.
+    configs = {}
+    if not args.no_configs:
+        from gym_fishing_b200.distributed import allreduce_stats
+        from gym_fishing_b200.rollouts import escapement_sweep, rollout_stats
+
+        def timed_call(fn, reps=3):
+            out = fn()                      # warm-up: allocator blocks, NCCL communicator
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(reps):
+                out = fn()
+            c1.record()
+            barrier()
+            return barrier_max_ms(c0.elapsed_time(c1) / reps, dev), out
+
+        S2 = float.fromhex("0x1.9374bcp-1")    # float32 BMSY of fishing-v2 (tests/golden/kat.json kat3b.S)
+        n3, T3 = args.cfg3_envs, 1000
+        ms3, r3 = timed_call(lambda: rollout_stats("fishing-v2", n3, T3, policy="escapement", S=S2, device=dev, seed=0,
+                                                   r=0.3, K=1.0, C=0.5, sigma=0.05, init_state=0.75, Tmax=1000))
+        configs["cfg3"] = {
+            "workload": f"fishing-v2 tipping point, {n3} envs total over {world} GPU(s), fused {T3}-step constant-escapement rollout, "
+                        "sigma=0.05, freeze on done; reset + K2 + K4 + all-gather of the [256,3] statistics inside the timed call",
+            "value": n3 * T3 / (ms3 * 1e-3), "unit": UNIT, "ms": ms3, "scaling": "strong",
+            "checksum": {"sum": float(r3["sum"]).hex(), "sumsq": float(r3["sumsq"]).hex(), "n_done": float(r3["n_done"])},
+            "mean_return": float(r3["mean"]), "std_return": float(r3["std"])}
+        L5, R5, T5 = 1024, args.cfg5_replicates, 1000
+        ms5, r5 = timed_call(lambda: escapement_sweep("fishing-v1", levels=L5, replicates=R5, T=T5, device=dev, seed=0,
+                                                      r=0.3, K=1.0, sigma=0.1, init_state=0.75, Tmax=1000))
+        # the collective alone: the [levels, 3] block of this rank through the same deterministic all-gather + tree
+        blk = torch.stack([r5["sum"], r5["sumsq"], r5["n_done"]], dim=1).contiguous()
+        allreduce_stats(blk)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            allreduce_stats(blk)
+        c1.record()
+        barrier()
+        coll_ms = barrier_max_ms(c0.elapsed_time(c1) / 10, dev)
+        best = int(torch.argmax(r5["mean"]).item())
+        configs["cfg5"] = {
+            "workload": f"escapement sweep: {L5} levels x {R5} replicates x {T5} steps of fishing-v1 (sigma=0.1, common random numbers), "
+                        f"replicates sharded over {world} GPU(s); reset + sweep kernel + K4 + all-gather of the [{L5},3] statistics inside the timed call",
+            "value": L5 * R5 * T5 / (ms5 * 1e-3), "unit": UNIT, "ms": ms5, "scaling": "strong",
+            "collective_ms": coll_ms if world > 1 else 0.0, "collective_share": (coll_ms / ms5) if world > 1 else 0.0,
+            "checksum": {"sum_of_sums": float(r5["sum"].sum()).hex(), "sumsq_17": float(r5["sumsq"][17]).hex(),
+                         "mean_200": float(r5["mean"][200]).hex(), "n_done": float(r5["n_done"].sum())},
+            "best_level": best, "best_S": float(r5["S"][best]), "best_mean_return": float(r5["mean"][best])}
+        del r3, r5, blk
+        torch.cuda.empty_cache()
+
     # ---- e2e: numpy host buffers through the C-ABI host front end (H2D of actions, D2H of obs/reward/done every lock-step)
     e2e_T = min(T, args.e2e_T)
     # host side of the copies: run on (and allocate the pinned buffers from) the cores next to this GPU; undone before the
@@ -457,13 +552,16 @@ def run_gpu(args):
             pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v1 = cpu_port_throughput(args.cpu_steps, 1)
-            cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{args.cpu_steps} env.step calls of the reference-shaped scalar port (oracle.ScalarPortEnv), fishing-v1 sigma=0.01",
+            have_ref = reference_available()
+            v1 = cpu_loop_throughput(_ref_worker if have_ref else _port_worker, args.cpu_steps, 1)
+            cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "reference" if have_ref else "port",
+                   "sample": f"{args.cpu_steps} env.step calls of " + ("the unmodified reference (baseline/_ref/gym_fishing under the oracle/refstub gym stand-in)"
+                                                                       if have_ref else "the reference-shaped scalar port (oracle.ScalarPortEnv)") + ", fishing-v1 sigma=0.01, one core",
+                   "scalar_port_1core": cpu_port_throughput(min(args.cpu_steps, 300_000), 1) if have_ref else None,
                    "numpy_vectorised_1core": cpu_vectorised_throughput(),
                    "c_openmp_all_cores": cpu_c_port_throughput(), "host_cores": os.cpu_count(),
-                   "note": "value = the reference-shaped port (what the reference itself achieves per core); the numpy-vectorised and "
-                           "C/OpenMP figures are best-effort CPU restatements with pre-generated noise, for context"}
+                   "note": "value = the reference's own step() loop on one core; scalar_port / numpy-vectorised / C-OpenMP are the oracle's "
+                           "restatements (pre-generated noise for the latter two), for context"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -480,6 +578,7 @@ def run_gpu(args):
                     "sb3_dtypes": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 9,
                                    "api": "FishingVecEnv(io='numpy', sb3_dtypes=True).step_many -> fishing_vec_step_many_f32 (float32 actions / obs / rewards, the dtypes a stable-baselines3 VecEnv exchanges)"}},
             "fused": fused,
+            "configs": configs,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),
             "check": {"frac_done_last_step": frac_done, "mean_reward_last_step": mean_rew},
@@ -502,6 +601,10 @@ def main():
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=1_000_000)
     ap.add_argument("--ref-steps-per-core", dest="ref_steps_per_core", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg5 legs")
+    ap.add_argument("--cfg3-envs", dest="cfg3_envs", type=int, default=1 << 24)
+    ap.add_argument("--cfg5-replicates", dest="cfg5_replicates", type=int, default=16384)
+    ap.add_argument("--ref-port", action="store_true", help="reference arm: time the oracle's scalar port even when baseline/_ref exists")
     ap.add_argument("--no-cpu-bind", action="store_true", help="do not pin the e2e section to the GPU-local cores")
     ap.add_argument("--no-graph", action="store_true", help="issue the K1 launches directly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -29,7 +29,7 @@ POLICY_ACTIONS, POLICY_ESCAPEMENT, POLICY_MSY = 0, 1, 2
 STREAM_STEP, STREAM_AUTORESET, STREAM_RESET = 0, 1, 2
 
 EXPORTS = (
-    "fishing_abi_version", "fishing_error_string", "fishing_launch_count", "fishing_reset", "fishing_step",
+    "fishing_abi_version", "fishing_build_id", "fishing_error_string", "fishing_launch_count", "fishing_reset", "fishing_step",
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
@@ -138,8 +138,22 @@ def lib():
     L.fishing_vec_soa.argtypes = [vp, C.POINTER(FishingSoA)]
     if L.fishing_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.fishing_abi_version()} != {ABI_VERSION}; rebuild")
+    L.fishing_build_id.restype = C.c_char_p
+    L.fishing_build_id.argtypes = []
+    if not os.environ.get("FISHING_B200_LIB") and os.environ.get("FISHING_ALLOW_STALE_LIB") != "1":
+        # the product library must have been compiled from THIS tree (an A/B build named by FISHING_B200_LIB is exempt)
+        from .build import source_id
+
+        have, want = L.fishing_build_id().decode(), source_id()
+        if have != want:
+            raise ImportError(f"{LIB_PATH} was built from other sources (build id {have}, tree {want}); run "
+                              "`python __graft_entry__.py build`, or set FISHING_ALLOW_STALE_LIB=1 to use it anyway")
     _lib = L
     return L
+
+
+def build_id():
+    return lib().fishing_build_id().decode()
 
 
 def check(code, where):

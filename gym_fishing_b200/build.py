@@ -1,6 +1,7 @@
 """In-tree build of libfishing_b200.so with nvcc for sm_100a (no JIT cache: the .so travels with the tree)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -17,12 +18,38 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
+_ID_MARK = b"FISHING_BUILD_ID="
+
+
+def source_id(extra_flags=()):
+    """16 hex digits over everything the library is compiled from (csrc/*, the public header, the nvcc flags).  The same
+    string is baked into the binary (fishing_build_id()), so a library can be checked against the tree it ships with."""
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(os.path.dirname(_HERE), "include", "fishing_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra_flags)).encode())
+    return h.hexdigest()[:16]
+
+
+def library_id(path=None):
+    """The build id baked into a built library (read from the file, without loading it); None if absent."""
+    path = path or OUT
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    k = blob.find(_ID_MARK)
+    return blob[k + len(_ID_MARK):k + len(_ID_MARK) + 16].decode("ascii", "replace") if k >= 0 else None
+
+
 def needs_build():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "fishing_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    """True when there is no library or it was compiled from other sources than the tree holds (by content, not by file
+    time: a copy to another machine scrambles the times)."""
+    return library_id(OUT) != source_id()
 
 
 def _run(cmd):
@@ -44,7 +71,8 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
 
     objdir = os.path.join(os.path.dirname(_HERE), "build", "obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas=-v"] if verbose else [])
+    flags = ([f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas=-v"] if verbose else []) +
+             ['-DFISHING_BUILD_ID_STR="' + source_id(extra_flags) + '"'])
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     cmds = [[_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", o] for s, o in zip(SOURCES, objs)]
     with ThreadPoolExecutor(len(cmds)) as ex:
@@ -57,11 +85,13 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
         failed, l = _run(cmd)
         log += l
     if failed:
-        if os.path.exists(out) and not force:
-            # e.g. a box without nvcc, or file times scrambled by a copy: keep the library that travelled with the tree
-            print("gym_fishing_b200.build: rebuild failed, keeping the existing library\n" + log[-400:])
+        # A library that does not match the tree must never be used silently: tests and benchmarks would run yesterday's
+        # kernels.  FISHING_ALLOW_STALE_LIB=1 is the explicit way out (e.g. a box without nvcc).
+        if os.path.exists(out) and os.environ.get("FISHING_ALLOW_STALE_LIB") == "1":
+            print("gym_fishing_b200.build: rebuild failed, FISHING_ALLOW_STALE_LIB=1: keeping the existing library\n" + log[-400:])
             return out
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + log[-4000:])
+        raise RuntimeError("nvcc failed (set FISHING_ALLOW_STALE_LIB=1 to keep a library built from other sources):\n" +
+                           " ".join(cmd) + "\n" + log[-4000:])
     os.replace(out + ".tmp", out)
     if verbose:
         print(log)

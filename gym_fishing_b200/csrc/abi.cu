@@ -162,6 +162,16 @@ extern "C" {
 
 int fishing_abi_version(void) { return FISHING_ABI_VERSION; }
 
+// hash of the sources this library was compiled from (gym_fishing_b200/build.py:source_id); the marker lets the build
+// script read it from the file without loading the library
+#ifndef FISHING_BUILD_ID_STR
+#define FISHING_BUILD_ID_STR "unknown"
+#endif
+const char* fishing_build_id(void) {
+  static const char id[] = "FISHING_BUILD_ID=" FISHING_BUILD_ID_STR;
+  return id + sizeof("FISHING_BUILD_ID=") - 1;
+}
+
 uint64_t fishing_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int fishing_probe_fp64(double* scratch, int32_t blocks, int32_t iters, void* stream) {

@@ -8,13 +8,23 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "dynamics.cuh"
 #include "kernel_args.cuh"
 #include "philox.cuh"
 
+#ifndef FISHING_K2_UNROLL
+#define FISHING_K2_UNROLL 2
+#endif
+#ifndef FISHING_K2_MINBLOCKS
+#define FISHING_K2_MINBLOCKS 0   // resident 128-thread blocks per SM the fused kernel is compiled for (0: no register cap)
+#endif
+
 namespace fishing {
+
+constexpr int K2_UNROLL = FISHING_K2_UNROLL;   // timing builds may unroll the fused loop (tools/ab_build.py)
 
 // FISHING_GENERIC_ROLLOUT=1 forces the generic K2 kernel (A/B checks of the fast path)
 static bool generic_only() {
@@ -304,20 +314,39 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 // is loop-invariant resolved at compile time and a handful of comparisons removed that can never fire:
 //   * max(x - h, 0.0) (base_fishing_env.py:118) is the identity because h = min(x, quota) <= x (or NaN) always;
 //   * "stock <= 0" is the negation of the comparison np.maximum already makes;
-//   * the lower clip of the action is dead for the escapement / MSY policies: a = q/K - 1 with q = max(., 0) >= 0.
+//   * the lower clip of the action is dead for the escapement / MSY policies: a = q/K - 1 with q = max(., 0) >= 0;
+//   * reward = max(h, 0.0) (base_fishing_env.py:74) is the identity when the stock is never negative: h = min(x, quota)
+//     with quota >= 0 always, and x = (s + 1) K >= +-0 from the second step on (s = x2 / K - 1 with x2 >= 0, K >= 0).  Only
+//     the state the caller hands in can hold a negative stock: such a thread runs its FIRST step with the comparison
+//     (SAFE = true, a rarely taken copy of the loop body) and joins the others afterwards.  Negative K (P_UNIFORM with
+//     kd.odd) keeps the comparison; a negative reset stock is routed to the generic kernel by launch_rollout_p.
+//   * the return is accumulated unconditionally; when later episodes must not count (plain mode) its value at the first
+//     `done` is kept aside, which costs one select less than gating the addition.
 // Results are bit-identical to the generic kernel (tests/test_gpu_parity.py runs both against the oracle).
 struct FastEnv {
-  double s, K, r, S, ret, quota_const;
+  double s, K, r, S, ret, ret_snap, quota_const;
   int years, done_step;
   bool frozen;
 };
+
+// see "reward" above: does this environment enter with a negative stock?  (Then its first step runs with the comparison.)
+template <int PM>
+__device__ __forceinline__ bool fast_env_enter(FastEnv& e) {
+  double x = __dadd_rn(e.s, 1.0);
+  if (PM != P_KONE) x = __dmul_rn(x, e.K);
+  e.ret = e.ret_snap = 0.0;
+  e.done_step = -1;
+  e.frozen = false;
+  e.quota_const = 0.0;
+  return x < 0.0;
+}
 
 // What happens to an environment whose episode ended: it keeps stepping (the reference's behaviour when a caller ignores
 // `done`), it is reset in place (VecEnv semantics), or it is frozen (return statistics of first episodes).  A template
 // parameter, so that the plain loop carries no `frozen` tests and the compiler does not have to unswitch the loop.
 enum : int { M_PLAIN = 0, M_AUTO_RESET = 1, M_FREEZE = 2 };
 
-template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
                                               uint64_t gid, double& reward_out, bool& done_out) {
   constexpr bool auto_reset = MODE == M_AUTO_RESET, freeze = MODE == M_FREEZE;
@@ -353,15 +382,18 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
   const double x2 = alive ? g : 0.0;
   const double s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, e.K, a.kd) : div_z(x2, e.K)), 1.0);
-  const double reward = py_max(h, 0.0);
+  const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;
   reward_out = reward;
   done_out = done;
-  if (auto_reset || e.done_step < 0) e.ret = __dadd_rn(e.ret, reward);
+  e.ret = __dadd_rn(e.ret, reward);
   e.s = s2;
   if (done) {
-    if (e.done_step < 0) e.done_step = t;
+    if (e.done_step < 0) {
+      e.done_step = t;
+      if (!auto_reset && !freeze) e.ret_snap = e.ret;
+    }
     if (auto_reset) {
       e.years = 0;
       if (PM == P_PERENV) {
@@ -380,18 +412,28 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
 }
 
-template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE>
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
                                               uint64_t gid) {
   double reward;
   bool done;
-  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e, action, z, t, gid, reward, done);
+  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e, action, z, t, gid, reward, done);
+}
+
+// the return to report: all episodes (auto-reset), or the first one (frozen environments stop accumulating by themselves)
+template <int MODE>
+__device__ __forceinline__ double fast_env_return(const FastEnv& e) {
+  return (MODE == M_PLAIN && e.done_step >= 0) ? e.ret_snap : e.ret;
 }
 
 // TRACE: per-step observation / reward / done rows [T, n] written with streaming stores (the rollout-buffer fill of a
 // whole chunk in one launch).  Not combined with freeze-on-done or an action trace; those go to the generic kernel.
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
-__global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel(const RolloutArgs a) {
+  // the Box-Muller tables, staged once per block for the T draws of every thread (normal.cuh)
+  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  SharedTabs tb = {};
+  if (NOISY) tb = stage_normal_tables<128>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
   Lanes L;
@@ -412,6 +454,7 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
   const uint64_t gid0 = (uint64_t)(a.env_id0 + L.i0), gid1 = (uint64_t)(a.env_id0 + L.i1);
 
   FastEnv e0, e1;
+  bool unsafe;
   {
     const double2 s = load2<double2>(a.state, L);
     const int2 y = load2<int2>(a.years, L);
@@ -428,10 +471,8 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
       const double2 S = load2<double2>(a.S_env, L);
       e0.S = S.x; e1.S = S.y;
     }
-    e0.ret = e1.ret = 0.0;
-    e0.done_step = e1.done_step = -1;
-    e0.frozen = e1.frozen = false;
-    e0.quota_const = e1.quota_const = 0.0;
+    unsafe = fast_env_enter<PM>(e0);
+    unsafe = fast_env_enter<PM>(e1) || unsafe;
     if (POLICY == FISHING_POLICY_MSY) {
       double unused;
       e0.quota_const = policy_quota_msy<PM>(a, e0.K, unused);
@@ -447,24 +488,25 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
   char* tr_rew = TRACE ? reinterpret_cast<char*>(a.trace_reward) + tid * 16 : nullptr;
   char* tr_done = TRACE ? reinterpret_cast<char*>(a.trace_done) + tid * 2 : nullptr;
 
-#pragma unroll 1
-  for (int t = 0; t < T; ++t) {
+  // one lock-step of the thread's two environments; returns true when the loop can stop (both frozen)
+  auto step = [&](int t, auto safe_tag) -> bool {
+    constexpr bool SAFE = decltype(safe_tag)::value;
     double2 act = act_next;
     if (POLICY == FISHING_POLICY_ACTIONS && t + 1 < T) act_next = load2_stream<double2>(act_base + (int64_t)(t + 1) * a.n, L);
     double z0 = 0.0, z1 = 0.0;
     if (NOISY) {
-      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP, tb);
       z0 = d.z0; z1 = d.z1;
     }
     if (MODE == M_FREEZE) {
-      if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
-      if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
-      if (e0.frozen && e1.frozen) break;
+      if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0);
+      if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1);
+      return e0.frozen && e1.frozen;
     } else if (TRACE) {
       double r0, r1;
       bool d0, d1;
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0, r0, d0);
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1, r1, d1);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, r0, d0);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, r1, d1);
       // adjacent-pair layout and all three rows present (launch_rollout_p checks both): one 16-byte / 16-byte / 2-byte
       // streaming store each through pointers that advance by one row per step
       __stcs(reinterpret_cast<double2*>(tr_obs), make_double2(e0.s, e1.s));
@@ -474,9 +516,19 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
       tr_rew += row_f64;
       tr_done += row_u8;
     } else {
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e0, act.x, z0, t, gid0);
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE>(a, e1, act.y, z1, t, gid1);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1);
     }
+    return false;
+  };
+  // the first step is peeled for every thread (so that the loop counter stays warp-uniform); a thread into which a negative
+  // stock came runs it with reward = max(h, 0.0)
+  bool stop = T <= 0;
+  if (!stop) stop = unsafe ? step(0, std::true_type()) : step(0, std::false_type());
+  if (!stop) {
+#pragma unroll K2_UNROLL
+    for (int t = 1; t < T; ++t)
+      if (step(t, std::false_type())) break;
   }
 
   store2<double2>(a.state, L, e0.s, e1.s);
@@ -485,7 +537,7 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
     store2<double2>(a.K_env, L, e0.K, e1.K);
     store2<double2>(a.r_env, L, e0.r, e1.r);
   }
-  if (a.out_return) store2<double2>(a.out_return, L, e0.ret, e1.ret);
+  if (a.out_return) store2<double2>(a.out_return, L, fast_env_return<MODE>(e0), fast_env_return<MODE>(e1));
   if (a.out_done_step) store2<int2>(a.out_done_step, L, e0.done_step, e1.done_step);
 }
 
@@ -497,6 +549,9 @@ __global__ void __launch_bounds__(128) rollout_fast_kernel(const RolloutArgs a) 
 // are strided by m/LV so that neighbouring threads touch neighbouring addresses.
 template <int GROWTH, int PM, bool NOISY, int LV, int MODE>
 __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a) {
+  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  SharedTabs tb = {};
+  if (NOISY) tb = stage_normal_tables<128>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = a.noise_id_div, mq = m / LV;
   if (tid >= (a.n >> 1) / LV) return;
@@ -504,6 +559,7 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
   const uint64_t noise_pair = (uint64_t)((a.env_id0 / m) >> 1) + (uint64_t)kp;
   FastEnv e[2 * LV];
   int64_t idx[2 * LV];
+  bool unsafe = false;
 #pragma unroll
   for (int l = 0; l < LV; ++l)
 #pragma unroll
@@ -516,17 +572,14 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
       v.K = PM == P_PERENV ? a.K_env[i] : a.K;
       v.r = PM == P_PERENV ? a.r_env[i] : a.r;
       v.S = a.S_env ? a.S_env[i] : a.S;
-      v.ret = 0.0;
-      v.done_step = -1;
-      v.frozen = false;
-      v.quota_const = 0.0;
+      unsafe = fast_env_enter<PM>(v) || unsafe;
     }
   const int T = (int)a.T;
-#pragma unroll 1
-  for (int t = 0; t < T; ++t) {
+  auto step = [&](int t, auto safe_tag) -> bool {
+    constexpr bool SAFE = decltype(safe_tag)::value;
     double z[2] = {0.0, 0.0};
     if (NOISY) {
-      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP);
+      const Normal2 d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)t, FISHING_STREAM_STEP, tb);
       z[0] = d.z0;
       z[1] = d.z1;
     }
@@ -534,11 +587,18 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
 #pragma unroll
     for (int k = 0; k < 2 * LV; ++k) {
       if (MODE != M_FREEZE || !e[k].frozen)
-        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e[k], 0.0, z[k & 1], t,
-                                                                           (uint64_t)(a.env_id0 + idx[k]));
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, SAFE>(a, e[k], 0.0, z[k & 1], t,
+                                                                                 (uint64_t)(a.env_id0 + idx[k]));
       all_frozen = all_frozen && e[k].frozen;
     }
-    if (all_frozen) break;
+    return all_frozen;
+  };
+  bool stop = T <= 0;   // first step peeled, see rollout_fast_kernel
+  if (!stop) stop = unsafe ? step(0, std::true_type()) : step(0, std::false_type());
+  if (!stop) {
+#pragma unroll 1
+    for (int t = 1; t < T; ++t)
+      if (step(t, std::false_type())) break;
   }
 #pragma unroll
   for (int k = 0; k < 2 * LV; ++k) {
@@ -549,7 +609,7 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
       a.K_env[i] = e[k].K;
       a.r_env[i] = e[k].r;
     }
-    if (a.out_return) a.out_return[i] = e[k].ret;
+    if (a.out_return) a.out_return[i] = fast_env_return<MODE>(e[k]);
     if (a.out_done_step) a.out_done_step[i] = e[k].done_step;
   }
 }
@@ -582,6 +642,9 @@ static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_
 // body is the noise-free dynamics plus four SHFL, at the register count -- and occupancy -- of the plain kernel.
 template <int GROWTH, int PM, bool NOISY, int MODE>
 __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutArgs a) {
+  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  SharedTabs tb = {};
+  if (NOISY) tb = stage_normal_tables<128>(s_tab);
   const unsigned full = 0xffffffffu;
   const int64_t m = a.noise_id_div;                      // levels, a multiple of 32
   const int64_t warps_per_pair = m >> 5;
@@ -599,18 +662,29 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
   e0.K = PM == P_PERENV ? a.K_env[i0] : a.K; e1.K = PM == P_PERENV ? a.K_env[i1] : a.K;
   e0.r = PM == P_PERENV ? a.r_env[i0] : a.r; e1.r = PM == P_PERENV ? a.r_env[i1] : a.r;
   e0.S = a.S_env ? a.S_env[i0] : a.S; e1.S = a.S_env ? a.S_env[i1] : a.S;
-  e0.ret = e1.ret = 0.0;
-  e0.done_step = e1.done_step = -1;
-  e0.frozen = e1.frozen = false;
-  e0.quota_const = e1.quota_const = 0.0;
+  bool unsafe = fast_env_enter<PM>(e0);
+  unsafe = fast_env_enter<PM>(e1) || unsafe;
   const int T = (int)a.T;
   bool all_done = false;
+  if (T > 0) {   // first step peeled (see rollout_fast_kernel); with the comparison when a negative stock came into the warp
+    Normal2 d;
+    d.z0 = d.z1 = 0.0;
+    if (NOISY) d = normal_pair_keys(a.keys, noise_pair, a.step0, FISHING_STREAM_STEP, tb);
+    if (__any_sync(full, unsafe)) {
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e0, 0.0, d.z0, 0, gid0);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e1, 0.0, d.z1, 0, gid1);
+    } else {
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, d.z0, 0, gid0);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, d.z1, 0, gid1);
+    }
+    all_done = MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen);
+  }
 #pragma unroll 1
-  for (int t0 = 0; t0 < T && !all_done; t0 += 32) {
+  for (int t0 = 1; t0 < T && !all_done; t0 += 32) {
     Normal2 d;
     d.z0 = d.z1 = 0.0;
     if (NOISY && t0 + lane < T)
-      d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)(t0 + lane), FISHING_STREAM_STEP);
+      d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)(t0 + lane), FISHING_STREAM_STEP, tb);
     const int nt = (T - t0 < 32) ? T - t0 : 32;
 #pragma unroll 1
     for (int dt = 0; dt < nt; ++dt) {
@@ -636,7 +710,7 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
     a.K_env[i0] = e0.K; a.K_env[i1] = e1.K;
     a.r_env[i0] = e0.r; a.r_env[i1] = e1.r;
   }
-  if (a.out_return) { a.out_return[i0] = e0.ret; a.out_return[i1] = e1.ret; }
+  if (a.out_return) { a.out_return[i0] = fast_env_return<MODE>(e0); a.out_return[i1] = fast_env_return<MODE>(e1); }
   if (a.out_done_step) { a.out_done_step[i0] = e0.done_step; a.out_done_step[i1] = e1.done_step; }
 }
 
@@ -677,7 +751,10 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
                              policy != FISHING_POLICY_MSY && a.noise_id_div <= 1;
   // noise-free runs with uniform parameters outside (K > 0, r >= 0) need the explicit x * 0 term of grow(): generic kernel
   const bool odd_noise_free = a.kd.odd && a.sigma == 0.0;
-  const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && !odd_noise_free && a.T <= 0x7fffffffLL &&
+  // auto-reset into a negative stock: the specialised kernels assume the reset state holds a stock >= 0 (see FastEnv)
+  const double x_reset = PM == P_UNIFORM ? (a.s_reset + 1.0) * a.K : a.s_reset + 1.0;
+  const bool neg_reset = (a.flags & FISHING_AUTO_RESET) && x_reset < 0.0;
+  const bool fast = !a.discrete && (!tracing || fast_trace_ok) && !a.noise && !odd_noise_free && !neg_reset && a.T <= 0x7fffffffLL &&
                     (policy != FISHING_POLICY_ACTIONS || a.action_dtype == FISHING_ACT_F64) && !generic_only();
   constexpr int SWEEP_LV = 4;
   const bool sweep = fast && policy == FISHING_POLICY_ESCAPEMENT && a.noise_id_div > 1 && sweep_mode() != 1;

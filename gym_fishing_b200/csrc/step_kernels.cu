@@ -125,13 +125,24 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
         prefetch_l2(reinterpret_cast<const double2*>(a.r_env) + j);
       }
     }
-    if (ext_noise) {
-      z = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
-    } else if (noisy) {
-      const Normal2 d = normal_pair_keys(a.keys, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
+    if (ext_noise) z = ld_stream(reinterpret_cast<const double2*>(a.noise) + j);
+  }
+#ifdef FISHING_K1_SMEM_TABLES
+  // timing build: the block stages the Box-Muller tables in shared memory instead of reading them through the L1
+  __shared__ double2 s_tab[NORMAL_TABLE_ENTRIES];
+  if (noisy && !ext_noise) {     // block-uniform
+    const SharedTabs tb = stage_normal_tables<BS>(s_tab);
+    if (live) {
+      const Normal2 d = normal_pair_keys(a.keys, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP, tb);
       z = make_double2(d.z0, d.z1);
     }
   }
+#else
+  if (live && noisy && !ext_noise) {
+    const Normal2 d = normal_pair_keys(a.keys, ((uint64_t)a.env_id0 >> 1) + (uint64_t)j, a.step_idx, FISHING_STREAM_STEP);
+    z = make_double2(d.z0, d.z1);
+  }
+#endif
   if (a.flags & STEP_FLAG_PDL) pdl_wait();
   // the fishing-v4 kernel keeps idle lanes alive: every warp of the block has to sign off at the end (reset job list)
   if (!live && PM != P_PERENV) return;

@@ -132,6 +132,9 @@ typedef struct fishing_soa {
 } fishing_soa;
 
 int fishing_abi_version(void);
+/* Identifier of the sources the library was compiled from (16 hex digits; gym_fishing_b200/build.py:source_id).  New in
+ * round 2: the Python loader refuses a library whose id differs from the tree it sits in.  No reference counterpart. */
+const char* fishing_build_id(void);
 const char* fishing_error_string(int code);
 
 /* Number of kernel launches issued through this library since it was loaded (all entry points). */

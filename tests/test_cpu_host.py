@@ -232,10 +232,13 @@ def test_hot_kernels_keep_their_register_budget():
             usage[name] = {k: int(v) for k, v in (kv.split(":") for kv in line.split() if ":" in kv and kv.split(":")[1].isdigit())}
     k1 = [u for n, u in usage.items() if "step_kernel_vec2ILi0ELi0ELi0E" in n]     # <LOGISTIC, P_KONE, F64>
     assert k1 and all(u["REG"] <= 32 and u["STACK"] == 0 for u in k1), k1
+    # round 2: the fused loop is unrolled twice and keeps its constants in registers (116 registers, 4 resident blocks per
+    # SM): the kernel is bound by instruction issue, not latency, and measured 2.90e11 env-steps/s against 2.77e11 at 46
+    # registers / 10 blocks; capping it at 80 or 64 registers spills and costs 13 - 20 % (profiles/ab_r02.md)
     fast = [u for n, u in usage.items() if "rollout_fast_kernelILi0ELi0E" in n]
-    assert fast and all(u["REG"] <= 64 and u["STACK"] == 0 for u in fast), fast
+    assert fast and all(u["REG"] <= 128 and u["STACK"] == 0 for u in fast), fast
     sweep = [u for n, u in usage.items() if "rollout_sweep_kernelILi0ELi0E" in n]
-    assert sweep and all(u["REG"] <= 128 and u["STACK"] == 0 for u in sweep), sweep
+    assert sweep and all(u["REG"] <= 168 and u["STACK"] == 0 for u in sweep), sweep   # 8 environments per thread, first step peeled
 
 
 def test_two_correction_quotient_is_correctly_rounded_in_exact_arithmetic():

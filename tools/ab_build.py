@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Builds timing variants of libfishing_b200.so into gym_fishing_b200/ab/ (git-ignored, shipped to the GPU box):
+    python tools/ab_build.py [name ...]
+Run one with FISHING_B200_LIB=gym_fishing_b200/ab/lib_<name>.so python tools/k2_bench.py.  These are measurement aids (what
+does the Philox block cost, what does the round-1 Box-Muller cost); only the default build is the product."""
+from __future__ import annotations
+
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gym_fishing_b200.build import build  # noqa: E402
+
+VARIANTS = {
+    "normal_v1": ["-DFISHING_NORMAL_V1"],                 # round-1 Box-Muller (58 FP64 instructions per pair of draws)
+    "rounds7": ["-DFISHING_PHILOX_ROUNDS=7"],             # NOT the product: the cost of three Philox rounds
+    "rounds0": ["-DFISHING_PHILOX_ROUNDS=0"],             # NOT the product: counter words straight into the Box-Muller
+    "split_mul": ["-DFISHING_AB_SPLIT_MUL"],              # mul.hi + mul.lo kept apart instead of IMAD.WIDE
+    "unroll1": ["-DFISHING_K2_UNROLL=1"],                 # the fused loop not unrolled (default: 2)
+    "mb6": ["-DFISHING_K2_MINBLOCKS=6"],                  # fused kernel capped at 80 registers (6 blocks of 128 per SM)
+    "mb8": ["-DFISHING_K2_MINBLOCKS=8"],                  # ... 64 registers
+    "mb10": ["-DFISHING_K2_MINBLOCKS=10"],                # ... 48 registers
+    "unroll4": ["-DFISHING_K2_UNROLL=4"],
+    "k1smem": ["-DFISHING_K1_SMEM_TABLES"],               # K1 stages the Box-Muller tables in shared memory per block
+}
+
+
+def main():
+    names = sys.argv[1:] or list(VARIANTS)
+    outdir = os.path.join(ROOT, "gym_fishing_b200", "ab")
+    os.makedirs(outdir, exist_ok=True)
+    for n in names:
+        out = os.path.join(outdir, f"lib_{n}.so")
+        build(force=True, extra_flags=VARIANTS[n], out=out)
+        print("built", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,11 @@ def main():
     ms, _ = timed(k1)
     res["k1_v1_us_per_launch"] = round(ms * 1e3 / Tk, 3)
     res["k1_hash"] = int((obs[-1].view(torch.int64) >> 11).sum())
+    # the same loop without process noise (no Philox, no Box-Muller): what the lock-step costs apart from the draws
+    b = EnvBatch(nat.V1, n, device=dev, auto_reset=True, r=0.3, K=1.0, sigma=0.0, x0=0.75, Tmax=100, seed=0)
+    b.reset()
+    ms, _ = timed(k1)
+    res["k1_v1_sigma0_us_per_launch"] = round(ms * 1e3 / Tk, 3)
     print(json.dumps(res))
 
 
