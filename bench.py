@@ -372,20 +372,7 @@ def run_gpu(args):
             fms = barrier_max_ms(f0.elapsed_time(f1) / reps, dev)
             fused[name] = {"value": world * n * T / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms}
             del out, b2
-        S = 0.49960005283355713  # float32 BMSY of the default logistic model (tests/golden/kat.json kat1.S)
-        b3 = EnvBatch(nat.V1, n, device=dev, env_id0=rank * n, seed=0, auto_reset=True, **CFG)
-        b3.reset()
-        b3.rollout(T, policy="escapement", S=S)
-        stream.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(3):
-            b3.rollout(T, policy="escapement", S=S)
-        f1.record(stream)
-        stream.synchronize()
-        fms = barrier_max_ms(f0.elapsed_time(f1) / 3, dev)
-        fused["escapement_in_kernel"] = {"value": world * n * T / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms}
-        # FP64-pipe roofline of the fused kernel: peak = a DFMA loop measured here, on this GPU, now
+        # FP64-pipe peak: a DFMA loop measured here, on this GPU, now
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         scratch = torch.zeros(256, dtype=torch.float64, device=dev)
         p_blocks, p_iters = sm_count * 8, 8192
@@ -401,17 +388,61 @@ def run_gpu(args):
             stream.synchronize()
             best = min(best, f0.elapsed_time(f1))
         peak_thread_ops = p_blocks * 256 * p_iters * 8 / (best * 1e-3)          # DFMA thread-instructions per second
-        alg_ops = 29          # fishing-v1 step 22 + continuous escapement policy 6 + return accumulation 1
-        exe_ops = 46.5        # FP64-pipe instructions executed per env-step: 93 per environment pair (SASS, profiles/)
-        per_gpu = n * T / (fms * 1e-3)
-        fused["roofline_fp64"] = {
-            "kernel": "rollout_fast_kernel<LOGISTIC,P_KONE,ESCAPEMENT,NOISY,AUTO_RESET>", "bound": "fp64 pipe",
-            "peak": peak_thread_ops, "unit": "fp64 thread-instr/s", "peak_source": "fishing_probe_fp64 (DFMA loop, this run)",
-            "alg_fp64_ops_per_env_step": alg_ops, "useful_frac": alg_ops * per_gpu / peak_thread_ops,
-            "executed_fp64_instr_per_env_step": exe_ops, "pipe_frac": exe_ops * per_gpu / peak_thread_ops,
-            "note": "executed - algorithmic = the in-kernel Philox/Box-Muller normal (29 fp64 instr per draw) less the "
-                    "divisions and multiplications by K = 1 that the specialised kernel drops"}
-    del obs, rew, done, b3
+
+        def fused_policy_leg(kind, name, mangled, S, alg_ops, auto_reset, freeze, **cfg):
+            """K2 with the in-kernel escapement policy + Philox noise, and its roofline: the instruction mix of the loop is
+            read from the binary that just ran (tools/sass_loop.py), the SM clock from NVML during the timed launches."""
+            b3 = EnvBatch(kind, n, device=dev, env_id0=rank * n, seed=0, auto_reset=auto_reset, **cfg)
+            b3.reset()
+            b3.rollout(T, policy="escapement", S=S, freeze_done=freeze)
+            stream.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local) as ck:
+                f0.record(stream)
+                for _ in range(5):
+                    b3.reset()
+                    b3.rollout(T, policy="escapement", S=S, freeze_done=freeze)
+                f1.record(stream)
+                stream.synchronize()
+            fms = barrier_max_ms(f0.elapsed_time(f1) / 5, dev)
+            per_gpu = n * T / (fms * 1e-3)
+            fused[name] = {"value": world * per_gpu, "unit": UNIT, "ms_per_step": fms}
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                from sass_loop import loop_mix
+
+                mix = list(loop_mix(nat.LIB_PATH, mangled).values())[0]
+                steps = max(1, round(mix["pipes"].get("imad.wide", 16) / 17))      # 16 wide multiplies + 1-2 per unrolled step
+                fp64 = mix["pipes"].get("fp64", 0) / steps / 2                      # per environment-step (a thread owns a pair)
+                alu = mix["pipes"].get("alu", 0) / steps / 2
+                mhz = ck.summary()["sm_mhz"] or 1965
+                pair_steps_per_smsp = (n / 2 / 32) * T / (sm_count * 4)
+                cyc = mhz * 1e6 * fms * 1e-3 / pair_steps_per_smsp
+                port = 2.03 * 2 * (fp64 + alu)             # cycles per pair-step the FP64 + ALU port needs (2.03 cycles each)
+                fused[name]["roofline"] = {
+                    "kernel": mangled, "bound": "issue port shared by the FP64 and ALU pipes",
+                    "why": "tools/issue_probe.cu on B200: DFMA alone 2.03 cycles, LOP3 alone 2.03, DFMA+LOP3 3.9 -- FP64 and ALU instructions "
+                           "never overlap, IMAD / IMAD.WIDE (Philox) do; so the loop needs 2.03 x (FP64 + ALU instructions) cycles",
+                    "instr_per_pair_step": mix["n"] / steps, "fp64_instr_per_env_step": fp64, "alu_instr_per_env_step": alu,
+                    "port_cycles_per_pair_step": port, "measured_cycles_per_pair_step": cyc, "sm_mhz": mhz,
+                    "achieved": per_gpu, "peak": per_gpu * cyc / port, "unit": UNIT, "frac": port / cyc,
+                    "fp64_pipe": {"peak": peak_thread_ops, "unit": "fp64 thread-instr/s", "peak_source": "fishing_probe_fp64 (DFMA loop, this run)",
+                                  "pipe_frac": fp64 * per_gpu / peak_thread_ops, "alg_fp64_ops_per_env_step": alg_ops,
+                                  "useful_frac": alg_ops * per_gpu / peak_thread_ops,
+                                  "note": "the north-star's 'FP64-pipe utilisation': executed FP64 instructions over the DFMA peak; it FELL "
+                                          "from 0.58 (round 1) because the Box-Muller now needs 28 instead of 58 FP64 instructions per pair of "
+                                          "draws, while the throughput rose -- the pipe cannot be filled next to the ALU work of Philox and "
+                                          "of the dynamics' selects, see `why`"}}
+            except Exception as exc:  # noqa: BLE001  (no cuobjdump on this machine)
+                fused[name]["roofline"] = {"unavailable": repr(exc)}
+            del b3
+
+        fused_policy_leg(nat.V1, "escapement_in_kernel", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi1ELb0EE",
+                         0.49960005283355713,      # float32 BMSY of the default logistic model (tests/golden/kat.json kat1.S)
+                         29, True, False, **CFG)   # fishing-v1 step 22 + continuous escapement policy 6 + return accumulation 1
+        fused_policy_leg(nat.V2, "tipping_escapement_in_kernel", "rollout_fast_kernelILi1ELi0ELi1ELb1ELi2ELb0EE",
+                         float.fromhex("0x1.9374bcp-1"), 31, False, True, r=0.3, K=1.0, C=0.5, sigma=0.05, x0=0.75, Tmax=1000)
+    del obs, rew, done
     torch.cuda.empty_cache()
 
     # ---- BASELINE.json configs 3 and 5 at FULL size, sharded over the ranks of this run (strong scaling: the global problem is
@@ -469,6 +500,28 @@ def run_gpu(args):
         del r3, r5, blk
         torch.cuda.empty_cache()
 
+    # ---- what the link alone can carry: the copies of the e2e section without any kernel, both directions in flight
+    # (tools/pcie_probe.py holds the standalone version, profiles/pcie_probe_r02.txt its records at N = 1 and N = 8)
+    def link_rate(h2d_b, d2h_b, n_env=n * 8, reps=6):
+        h_in = torch.empty(int(n_env * h2d_b), dtype=torch.uint8).pin_memory()
+        d_in = torch.empty_like(h_in, device=dev)
+        d_out = torch.empty(int(n_env * d2h_b), dtype=torch.uint8, device=dev)
+        h_out = torch.empty(d_out.numel(), dtype=torch.uint8).pin_memory()
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        best = 0.0
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev) * 1e-3
+            best = max(best, world * n_env * reps / dt)
+        return best
+
     # ---- e2e: numpy host buffers through the C-ABI host front end (H2D of actions, D2H of obs/reward/done every lock-step)
     e2e_T = min(T, args.e2e_T)
     # host side of the copies: run on (and allocate the pinned buffers from) the cores next to this GPU; undone before the
@@ -484,9 +537,9 @@ def run_gpu(args):
 
     from gym_fishing_b200.vec_env import _PinnedArray
 
-    pinned = _PinnedArray(n * 8, np.float64)
-    h_act = pinned.array.reshape(8, n)
-    h_act[:] = np.random.default_rng(rank).uniform(-1, 1, size=(8, n))
+    pinned = _PinnedArray(n * args.e2e_chunk, np.float64)
+    h_act = pinned.array.reshape(args.e2e_chunk, n)
+    h_act[:] = np.random.default_rng(rank).uniform(-1, 1, size=(args.e2e_chunk, n))
     for t in range(3):
         venv.step(h_act[t % 8])
     barrier()
@@ -500,7 +553,7 @@ def run_gpu(args):
     per_step_ms = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev)
     e2e_per_step = world * n * per_step_T / (per_step_ms * 1e-3)
     # whole-rollout host call: actions [T, n] in pinned host memory -> obs / reward / done [T, n] in pinned host memory
-    chunk_T = 8
+    chunk_T = args.e2e_chunk
     p_obs, p_rew, p_done = _PinnedArray(chunk_T * n, np.float64), _PinnedArray(chunk_T * n, np.float64), _PinnedArray(chunk_T * n, np.uint8)
     outs = (p_obs.array.reshape(chunk_T, n), p_rew.array.reshape(chunk_T, n), p_done.array.reshape(chunk_T, n))
     venv.step_many(h_act, out=outs)
@@ -536,9 +589,25 @@ def run_gpu(args):
     e2e32_ms = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev)
     e2e32_value = world * n * e2e_T / (e2e32_ms * 1e-3)
     venv32.close()
-    for pa in (p_act32, q_obs, q_rew, q_done):
+    # float32 + bit-packed dones: 4 B in, 8.125 B out per env-step
+    venvp = FishingVecEnv("fishing-v1", num_envs=n, device=dev, io="numpy", seed=0, auto_reset=True, env_id_offset=rank * n,
+                          sb3_dtypes=True, packed_done=True, r=CFG["r"], K=1, sigma=CFG["sigma"], init_state=CFG["x0"], Tmax=CFG["Tmax"])
+    venvp.reset()
+    q_bits = _PinnedArray(chunk_T * ((n + 7) // 8), np.uint8)
+    outsp = (outs32[0], outs32[1], q_bits.array.reshape(chunk_T, (n + 7) // 8))
+    venvp.step_many(a32, out=outsp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_T // chunk_T):
+        venvp.step_many(a32, out=outsp)
+    torch.cuda.synchronize()
+    e2ep_ms = barrier_max_ms((time.perf_counter() - t0) * 1e3, dev)
+    e2ep_value = world * n * e2e_T / (e2ep_ms * 1e-3)
+    venvp.close()
+    for pa in (p_act32, q_obs, q_rew, q_done, q_bits):
         pa.free()
     pinned.free()
+    link_f64, link_f32, link_packed = link_rate(8, 17), link_rate(4, 9), link_rate(4, 8.125)
     os.sched_setaffinity(0, affinity0)
 
     if rank == 0:
@@ -573,10 +642,17 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
                     "lock_steps_timed": e2e_T, "host_cores_bound_to_gpu_numa_node": bound_cpus,
-                    "api": "FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, 8 lock-steps per call)",
+                    "api": f"FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, {args.e2e_chunk} lock-steps per call: one strided H2D and three strided D2H copies per third of the batch)",
                     "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"},
+                    "link_only": {"value": link_f64, "unit": UNIT,
+                                  "what": "the same 8 B in / 17 B out per env-step as bare pinned-memory copies, both directions in flight, no kernels"},
+                    "frac_of_pcie": e2e_value / link_f64,
                     "sb3_dtypes": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 9,
-                                   "api": "FishingVecEnv(io='numpy', sb3_dtypes=True).step_many -> fishing_vec_step_many_f32 (float32 actions / obs / rewards, the dtypes a stable-baselines3 VecEnv exchanges)"}},
+                                   "link_only": link_f32, "frac_of_pcie": e2e32_value / link_f32,
+                                   "api": "FishingVecEnv(io='numpy', sb3_dtypes=True).step_many -> fishing_vec_step_many_f32 (float32 actions / obs / rewards, the dtypes a stable-baselines3 VecEnv exchanges)"},
+                    "sb3_dtypes_packed_done": {"value": e2ep_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * 8 + (n + 7) // 8,
+                                               "link_only": link_packed, "frac_of_pcie": e2ep_value / link_packed,
+                                               "api": "FishingVecEnv(io='numpy', sb3_dtypes=True, packed_done=True).step_many -> fishing_vec_step_many_wire (dones cross PCIe bit-packed; unpacking on the host is not timed)"}},
             "fused": fused,
             "configs": configs,
             "gpu_launches": int(launches_per_step * args.steps),
@@ -597,7 +673,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--T", type=int, default=1000)
-    ap.add_argument("--e2e-T", dest="e2e_T", type=int, default=200)
+    ap.add_argument("--e2e-T", dest="e2e_T", type=int, default=256)
+    ap.add_argument("--e2e-chunk", dest="e2e_chunk", type=int, default=32, help="lock-steps per fishing_vec_step_many call")
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=1_000_000)
     ap.add_argument("--ref-steps-per-core", dest="ref_steps_per_core", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -22,18 +22,21 @@ LOGNORMAL_KINDS = (V5, V6, V7, V8, V9, V10, V11)
 FN_ALLEN, FN_BEVERTON_HOLT, FN_MYERS, FN_MAY, FN_RICKER = 0, 1, 2, 3, 4
 FN_OF_NAME = {"allen": FN_ALLEN, "beverton_holt": FN_BEVERTON_HOLT, "myers": FN_MYERS, "may": FN_MAY, "ricker": FN_RICKER}
 MAX_MODELS = 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_F64, ACT_F32, ACT_I32, ACT_I64 = 0, 1, 2, 3
 AUTO_RESET, FREEZE_DONE = 1, 2
 POLICY_ACTIONS, POLICY_ESCAPEMENT, POLICY_MSY = 0, 1, 2
 STREAM_STEP, STREAM_AUTORESET, STREAM_RESET = 0, 1, 2
+WIRE_OBS_F32, WIRE_REWARD_F32, WIRE_DONE_BITS = 1, 2, 4
+ARRAY_STATE, ARRAY_YEARS, ARRAY_K, ARRAY_R, ARRAY_MODEL, ARRAY_TERMINAL = 0, 1, 2, 3, 4, 5
 
 EXPORTS = (
     "fishing_abi_version", "fishing_build_id", "fishing_error_string", "fishing_launch_count", "fishing_reset", "fishing_step",
     "fishing_noise_fill", "fishing_rollout", "fishing_reduce_scratch_bytes", "fishing_reduce_stats", "fishing_bmsy",
     "fishing_vec_create", "fishing_vec_destroy", "fishing_vec_reset", "fishing_vec_step", "fishing_host_alloc",
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
-    "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32", "fishing_probe_fp64",
+    "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32", "fishing_probe_fp64", "fishing_step_ex",
+    "fishing_vec_step_many_wire", "fishing_vec_fetch_array", "fishing_vec_store_array", "fishing_vec_set_params",
 )
 
 
@@ -54,6 +57,11 @@ class FishingParams(C.Structure):
 class FishingSoA(C.Structure):
     _fields_ = [("state", C.c_void_p), ("years", C.c_void_p), ("K_env", C.c_void_p), ("r_env", C.c_void_p),
                 ("model", C.c_void_p)]
+
+
+class FishingStepExtra(C.Structure):
+    _fields_ = [("ep_return", C.c_void_p), ("last_ep_return", C.c_void_p), ("last_ep_length", C.c_void_p),
+                ("out_obs32", C.c_void_p), ("out_reward32", C.c_void_p), ("out_done_bits", C.c_void_p)]
 
 
 class FishingRolloutArgs(C.Structure):
@@ -102,12 +110,22 @@ def lib():
     L.fishing_population_draw_ln.argtypes = [P, i32, i64, vp, vp, vp, vp]
     L.fishing_step.restype = C.c_int
     L.fishing_step.argtypes = [P, i64, i64, u64, vp, i32, vp, vp, FishingSoA, vp, vp, vp, vp, vp, vp, vp]
+    L.fishing_step_ex.restype = C.c_int
+    L.fishing_step_ex.argtypes = [P, i64, i64, u64, vp, i32, vp, vp, FishingSoA, vp, vp, vp, vp, C.POINTER(FishingStepExtra), vp]
     L.fishing_step_many.restype = C.c_int
     L.fishing_step_many.argtypes = [P, i64, i64, u64, i64, vp, i32, vp, FishingSoA, vp, vp, vp, vp, vp]
     L.fishing_vec_step_many.restype = C.c_int
     L.fishing_vec_step_many.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     L.fishing_vec_step_many_f32.restype = C.c_int
     L.fishing_vec_step_many_f32.argtypes = [vp, i64, vp, i32, vp, vp, vp]
+    L.fishing_vec_step_many_wire.restype = C.c_int
+    L.fishing_vec_step_many_wire.argtypes = [vp, i64, vp, i32, vp, vp, vp, C.c_uint32]
+    L.fishing_vec_fetch_array.restype = C.c_int
+    L.fishing_vec_fetch_array.argtypes = [vp, i32, vp]
+    L.fishing_vec_store_array.restype = C.c_int
+    L.fishing_vec_store_array.argtypes = [vp, i32, vp]
+    L.fishing_vec_set_params.restype = C.c_int
+    L.fishing_vec_set_params.argtypes = [vp, P]
     L.fishing_vec_fetch_terminal.restype = C.c_int
     L.fishing_vec_fetch_terminal.argtypes = [vp, vp]
     L.fishing_noise_fill.restype = C.c_int

@@ -231,7 +231,7 @@ static int reset_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint6
 static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                      int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                      double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
-                     double* out_obs2, void* stream);
+                     double* out_obs2, void* stream, const fishing_step_extra* x = nullptr);
 
 int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                  int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
@@ -241,12 +241,27 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
                    out_terminal, out_stock, out_harvest, nullptr, stream);
 }
 
+int fishing_step_ex(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                    int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
+                    double* out_reward, uint8_t* out_done, double* out_terminal, const fishing_step_extra* x, void* stream) {
+  return step_impl(p, n, env_id0, step_idx, action, action_dtype, noise, reset_noise, soa, out_obs, out_reward, out_done,
+                   out_terminal, nullptr, nullptr, nullptr, stream, x);
+}
+
 static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
                      int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
                      double* out_reward, uint8_t* out_done, double* out_terminal, double* out_stock, double* out_harvest,
-                     double* out_obs2, void* stream) {
+                     double* out_obs2, void* stream, const fishing_step_extra* x) {
   if (!p || n < 0 || env_id0 < 0 || !kind_ok(p->kind) || !action || !out_obs || !out_reward || !out_done)
     return FISHING_E_ARG;
+  if (x) {
+    const int have = (x->ep_return != nullptr) + (x->last_ep_return != nullptr) + (x->last_ep_length != nullptr);
+    if (have != 0 && have != 3) return FISHING_E_ARG;
+    if ((x->ep_return && !aligned(x->ep_return, 8)) || (x->last_ep_return && !aligned(x->last_ep_return, 8)) ||
+        (x->last_ep_length && !aligned(x->last_ep_length, 4)) || (x->out_obs32 && !aligned(x->out_obs32, 4)) ||
+        (x->out_reward32 && !aligned(x->out_reward32, 4)) || (x->out_done_bits && !aligned(x->out_done_bits, 8)))
+      return FISHING_E_ALIGN;
+  }
   const int asz = act_size(action_dtype);
   if (!asz) return FISHING_E_ARG;
   if (!act_matches_kind(p->kind, action_dtype)) return FISHING_E_KIND;
@@ -270,6 +285,12 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   a.out_obs = out_obs; a.out_reward = out_reward; a.out_done = out_done; a.out_terminal = out_terminal;
   a.out_stock = out_stock; a.out_harvest = out_harvest;
   a.out_obs2 = out_obs2;
+  a.ep_return = x ? x->ep_return : nullptr;
+  a.last_ep_return = x ? x->last_ep_return : nullptr;
+  a.last_ep_length = x ? x->last_ep_length : nullptr;
+  a.out_obs32 = x ? x->out_obs32 : nullptr;
+  a.out_reward32 = x ? x->out_reward32 : nullptr;
+  a.out_done_bits = x ? reinterpret_cast<unsigned long long*>(x->out_done_bits) : nullptr;
   a.gp = growth_of(p);
   a.keys = philox_round_keys(p->seed);
   a.model = soa.model;
@@ -285,10 +306,13 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
              (!noise || aligned(noise, 16)) && (!out_stock || aligned(out_stock, 16)) &&
-             (!out_harvest || aligned(out_harvest, 16)) && (!out_obs2 || aligned(out_obs2, 16));
+             (!out_harvest || aligned(out_harvest, 16)) && (!out_obs2 || aligned(out_obs2, 16)) &&
+             (!a.ep_return || aligned(a.ep_return, 16)) && (!a.out_obs32 || aligned(a.out_obs32, 8)) &&
+             (!a.out_reward32 || aligned(a.out_reward32, 8));
   if (p->kind == FISHING_V4) vec = vec && aligned(soa.K_env, 16) && aligned(soa.r_env, 16);
   if (p->kind == FISHING_V11) vec = vec && aligned(soa.model, 8);
   if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
+  if (a.out_done_bits && !vec) return FISHING_E_ALIGN;   // the bit packing is a warp ballot of the pair-per-thread kernel
   if (vec && (p->flags & FISHING_PDL) && pdl_enabled()) a.flags |= STEP_FLAG_PDL;
   return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
 }
@@ -412,6 +436,9 @@ int fishing_reduce_stats(const double* ret, const int32_t* done_step, int64_t n,
 int fishing_population_draw(const fishing_params* p, int64_t n, const void* x, int32_t is_f32, double z, void* out,
                             void* stream) {
   if (!p || !kind_ok(p->kind) || n < 0 || !x || !out) return FISHING_E_ARG;
+  // the log-normal family (fishing-v5..v11) has its own growth functions: fishing_population_draw_ln.  The kernel behind
+  // this entry point only knows the logistic and tipping-point models and would silently return a logistic draw.
+  if (is_lognormal(p->kind)) return FISHING_E_KIND;
   if (!aligned(x, is_f32 ? 4 : 8) || !aligned(out, is_f32 ? 4 : 8)) return FISHING_E_ALIGN;
   if (n == 0) return 0;
   return (int)launch_growth(p->kind, n, x, is_f32 != 0, p->r, p->K, p->C, p->sigma, z, out,
@@ -450,6 +477,7 @@ int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int
 
 int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out) {
   if (!kind_ok(kind) || !S_out) return FISHING_E_ARG;
+  if (is_lognormal(kind)) return FISHING_E_KIND;   // no logistic BMSY for fishing-v5..v11 (models/policies.py evaluates theirs)
   double* dev = nullptr;
   cudaError_t e = cudaMalloc(&dev, 2 * sizeof(double));
   if (e != cudaSuccess) return (int)e;
@@ -478,8 +506,15 @@ struct fishing_vec {
   double* d_reward;
   uint8_t* d_done;
   double* d_terminal;
-  float* d_obs32;      // float32 staging for the stable-baselines3-dtype front end (allocated on first use)
-  float* d_reward32;
+  // staging of fishing_vec_step_many*: [T, chunk] blocks per pipeline chunk, grown on demand
+  char* m_action;      // T * n * 8
+  double* m_obs;       // T * n
+  double* m_reward;
+  uint8_t* m_done;
+  float* m_obs32;      // only for the float32 wire formats
+  float* m_reward32;
+  uint64_t* m_bits;    // only for bit-packed dones: T * words(n)
+  int64_t m_T, m_T32, m_Tbits;   // rows the three groups are currently sized for
   cudaStream_t streams[3];
   cudaEvent_t ev[3];
   int64_t chunk;       // environments per pipeline chunk (even)
@@ -489,7 +524,8 @@ static void vec_free(fishing_vec* v) {
   if (!v) return;
   cudaFree(v->soa.state); cudaFree(v->soa.years); cudaFree(v->soa.K_env); cudaFree(v->soa.r_env); cudaFree(v->soa.model);
   cudaFree(v->d_action); cudaFree(v->d_noise); cudaFree(v->d_reward); cudaFree(v->d_done); cudaFree(v->d_terminal);
-  cudaFree(v->d_obs32); cudaFree(v->d_reward32);
+  cudaFree(v->m_action); cudaFree(v->m_obs); cudaFree(v->m_reward); cudaFree(v->m_done);
+  cudaFree(v->m_obs32); cudaFree(v->m_reward32); cudaFree(v->m_bits);
   for (int i = 0; i < 3; ++i) {
     if (v->streams[i]) cudaStreamDestroy(v->streams[i]);
     if (v->ev[i]) cudaEventDestroy(v->ev[i]);
@@ -524,7 +560,13 @@ int fishing_vec_create(const fishing_params* p, int64_t n, int64_t env_id0, int3
     return e != cudaSuccess ? (int)e : (int)cudaErrorMemoryAllocation;
   }
   v->d_obs = v->soa.state;
-  cudaMemset(v->d_terminal, 0xFF, nd);  // NaN until an episode actually ends
+  // NaN until an episode actually ends; on the stream the first step will use (the handle's streams are non-blocking, so
+  // a legacy-stream memset would not be ordered against them)
+  if (cudaMemsetAsync(v->d_terminal, 0xFF, nd, v->streams[0]) != cudaSuccess || cudaStreamSynchronize(v->streams[0]) != cudaSuccess) {
+    e = cudaGetLastError();
+    vec_free(v);
+    return e != cudaSuccess ? (int)e : (int)cudaErrorUnknown;
+  }
   // a few chunks in flight hide the first H2D / last D2H; chunks stay even and 16-byte aligned
   int64_t nchunks = 2;
   if (const char* e = std::getenv("FISHING_VEC_CHUNKS")) {
@@ -569,6 +611,15 @@ int fishing_vec_reset(fishing_vec* v, double* obs_out) {
   return (int)cudaStreamSynchronize(st);
 }
 
+// bookkeeping after one successful lock-step of the whole batch
+static void vec_advance(fishing_vec* v) {
+  v->step_idx += 1;
+  if (v->p.kind == FISHING_V10) {   // r <- r + alpha, sequential adds like the reference (growth_models.py:147-150)
+    volatile double r_next = v->p.r + v->p.alpha;
+    v->p.r = r_next;
+  }
+}
+
 int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, const double* noise, double* obs_out,
                      double* reward_out, uint8_t* done_out, double* terminal_out) {
   if (!v || !action || !obs_out || !reward_out || !done_out) return FISHING_E_ARG;
@@ -597,11 +648,7 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
                      nullptr, static_cast<double*>(d_obs), v->streams[0]);
       e = cudaStreamSynchronize(v->streams[0]);
       if (e != cudaSuccess && rc == 0) rc = (int)e;
-      v->step_idx += 1;
-      if (v->p.kind == FISHING_V10) {
-        volatile double r_next = v->p.r + v->p.alpha;
-        v->p.r = r_next;
-      }
+      if (rc == 0) vec_advance(v);     // a failed step leaves the counters where they were
       return rc;
     }
   }
@@ -633,10 +680,147 @@ int fishing_vec_step(fishing_vec* v, const void* action, int32_t action_dtype, c
     e = cudaStreamSynchronize(v->streams[i]);
     if (e != cudaSuccess && rc == 0) rc = (int)e;
   }
-  v->step_idx += 1;
-  if (v->p.kind == FISHING_V10) {
-    volatile double r_next = v->p.r + v->p.alpha;
-    v->p.r = r_next;
+  if (rc == 0) vec_advance(v);
+  return rc;
+}
+
+// Grow the [T, n] staging blocks.  Each group is allocated as a whole or not at all (a half-grown group is never left behind).
+static int vec_ensure_staging(fishing_vec* v, int64_t T, uint32_t wire) {
+  const size_t n = (size_t)v->n;
+  if (T > v->m_T) {
+    cudaFree(v->m_action); cudaFree(v->m_obs); cudaFree(v->m_reward); cudaFree(v->m_done);
+    v->m_action = nullptr; v->m_obs = nullptr; v->m_reward = nullptr; v->m_done = nullptr; v->m_T = 0;
+    if (cudaMalloc(&v->m_action, T * n * 8) != cudaSuccess || cudaMalloc(&v->m_obs, T * n * 8) != cudaSuccess ||
+        cudaMalloc(&v->m_reward, T * n * 8) != cudaSuccess || cudaMalloc(&v->m_done, T * n) != cudaSuccess) {
+      cudaFree(v->m_action); cudaFree(v->m_obs); cudaFree(v->m_reward); cudaFree(v->m_done);
+      v->m_action = nullptr; v->m_obs = nullptr; v->m_reward = nullptr; v->m_done = nullptr;
+      cudaGetLastError();
+      return (int)cudaErrorMemoryAllocation;
+    }
+    v->m_T = T;
+  }
+  if ((wire & (FISHING_WIRE_OBS_F32 | FISHING_WIRE_REWARD_F32)) && T > v->m_T32) {
+    cudaFree(v->m_obs32); cudaFree(v->m_reward32);
+    v->m_obs32 = nullptr; v->m_reward32 = nullptr; v->m_T32 = 0;
+    if (cudaMalloc(&v->m_obs32, T * n * 4) != cudaSuccess || cudaMalloc(&v->m_reward32, T * n * 4) != cudaSuccess) {
+      cudaFree(v->m_obs32); cudaFree(v->m_reward32);
+      v->m_obs32 = nullptr; v->m_reward32 = nullptr;
+      cudaGetLastError();
+      return (int)cudaErrorMemoryAllocation;
+    }
+    v->m_T32 = T;
+  }
+  if ((wire & FISHING_WIRE_DONE_BITS) && T > v->m_Tbits) {
+    cudaFree(v->m_bits);
+    v->m_bits = nullptr; v->m_Tbits = 0;
+    // every pipeline chunk rounds its row up to whole 64-bit words: at most 64 extra words per row
+    if (cudaMalloc(&v->m_bits, T * ((n + 63) / 64 + 64) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      return (int)cudaErrorMemoryAllocation;
+    }
+    v->m_Tbits = T;
+  }
+  return 0;
+}
+
+// T lock-steps with host arrays.  The environment range is cut into chunks that rotate over three streams; a chunk's whole
+// [T, len] action block comes over in ONE strided copy, its T kernels run back to back (programmatic dependent launch between
+// them, row t of the observation block is the state of step t + 1), and every output array goes back in ONE strided copy:
+// 4 transfers per chunk whatever T is, large enough to run at the link rate, with the chunks on the other two streams
+// keeping both copy engines and the SMs busy meanwhile.
+static int vec_step_many_core(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, void* obs_out,
+                              void* reward_out, void* done_out, uint32_t wire) {
+  if (!v || !actions || !obs_out || !reward_out || !done_out || T < 0) return FISHING_E_ARG;
+  if (wire & ~(uint32_t)(FISHING_WIRE_OBS_F32 | FISHING_WIRE_REWARD_F32 | FISHING_WIRE_DONE_BITS)) return FISHING_E_ARG;
+  if (!v->was_reset) return FISHING_E_STATE;
+  const int asz = act_size(action_dtype);
+  if (!asz) return FISHING_E_ARG;
+  if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
+  const int64_t n = v->n;
+  if ((wire & FISHING_WIRE_DONE_BITS) && (n % 2 != 0 || v->env_id0 % 2 != 0)) return FISHING_E_ALIGN;
+  if (T == 0) return 0;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  if (int rc = vec_ensure_staging(v, T, wire)) return rc;
+  const bool obs32 = wire & FISHING_WIRE_OBS_F32, rew32 = wire & FISHING_WIRE_REWARD_F32, bits = wire & FISHING_WIRE_DONE_BITS;
+  const size_t osz = obs32 ? 4 : 8, rsz = rew32 ? 4 : 8;
+  const size_t host_bits_row = (size_t)(n + 7) / 8;
+  // six chunks over three streams by default: the first action block (nothing can overlap it) is a sixth of the batch
+  static const int64_t nchunks = [] {
+    const char* e = std::getenv("FISHING_VEC_MANY_CHUNKS");
+    const long c = e ? std::atol(e) : 6;
+    return (int64_t)((c >= 1 && c <= 64) ? c : 6);
+  }();
+  int64_t chunk = ((n + nchunks - 1) / nchunks + 1023) / 1024 * 1024;
+  if (chunk > n) chunk = n;
+  int rc = 0;
+  double r_after = v->p.r;
+  int k = 0;
+  int64_t bit_words_before = 0;   // words of bit rows of the chunks before this one
+  for (int64_t off = 0; off < n && rc == 0; off += chunk, ++k) {
+    const int64_t len = (n - off < chunk) ? n - off : chunk;
+    const int64_t words = (len + 63) / 64;
+    cudaStream_t st = v->streams[k % 3];
+    char* d_act = v->m_action + (size_t)T * off * asz;
+    double* d_obs = v->m_obs + (size_t)T * off;
+    double* d_rew = v->m_reward + (size_t)T * off;
+    uint8_t* d_done = v->m_done + (size_t)T * off;
+    float* d_obs32 = obs32 ? v->m_obs32 + (size_t)T * off : nullptr;
+    float* d_rew32 = rew32 ? v->m_reward32 + (size_t)T * off : nullptr;
+    uint64_t* d_bits = bits ? v->m_bits + (size_t)T * bit_words_before : nullptr;
+    e = cudaMemcpy2DAsync(d_act, (size_t)len * asz, static_cast<const char*>(actions) + (size_t)off * asz, (size_t)n * asz,
+                          (size_t)len * asz, (size_t)T, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = (int)e; break; }
+    fishing_soa cur = v->soa;
+    cur.state += off; cur.years += off;
+    if (cur.K_env) { cur.K_env += off; cur.r_env += off; }
+    if (cur.model) cur.model += off;
+    double* const state_home = cur.state;
+    fishing_params q = v->p;
+    for (int64_t t = 0; t < T && rc == 0; ++t) {
+      q.flags = (v->p.flags & ~(uint32_t)FISHING_PDL) | (t > 0 ? (uint32_t)FISHING_PDL : 0u);
+      fishing_step_extra x = {};
+      x.out_obs32 = d_obs32 ? d_obs32 + t * len : nullptr;
+      x.out_reward32 = d_rew32 ? d_rew32 + t * len : nullptr;
+      x.out_done_bits = d_bits ? d_bits + t * words : nullptr;
+      rc = step_impl(&q, len, v->env_id0 + off, v->step_idx + (uint64_t)t, d_act + (size_t)t * len * asz, action_dtype, nullptr,
+                     nullptr, cur, d_obs + t * len, d_rew + t * len, d_done + t * len, v->d_terminal + off, nullptr, nullptr,
+                     nullptr, st, wire ? &x : nullptr);
+      cur.state = d_obs + t * len;
+      if (q.kind == FISHING_V10) {
+        volatile double r_next = q.r + q.alpha;
+        q.r = r_next;
+      }
+    }
+    if (rc) break;
+    r_after = q.r;
+    e = cudaMemcpyAsync(state_home, cur.state, (size_t)len * 8, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+      e = obs32 ? cudaMemcpy2DAsync(static_cast<char*>(obs_out) + (size_t)off * 4, (size_t)n * 4, d_obs32, (size_t)len * 4,
+                                    (size_t)len * 4, (size_t)T, cudaMemcpyDeviceToHost, st)
+                : cudaMemcpy2DAsync(static_cast<char*>(obs_out) + (size_t)off * 8, (size_t)n * 8, d_obs, (size_t)len * 8,
+                                    (size_t)len * 8, (size_t)T, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = rew32 ? cudaMemcpy2DAsync(static_cast<char*>(reward_out) + (size_t)off * 4, (size_t)n * 4, d_rew32, (size_t)len * 4,
+                                    (size_t)len * 4, (size_t)T, cudaMemcpyDeviceToHost, st)
+                : cudaMemcpy2DAsync(static_cast<char*>(reward_out) + (size_t)off * 8, (size_t)n * 8, d_rew, (size_t)len * 8,
+                                    (size_t)len * 8, (size_t)T, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = bits ? cudaMemcpy2DAsync(static_cast<char*>(done_out) + (size_t)off / 8, host_bits_row, d_bits, (size_t)words * 8,
+                                   (size_t)(len + 7) / 8, (size_t)T, cudaMemcpyDeviceToHost, st)
+               : cudaMemcpy2DAsync(static_cast<char*>(done_out) + (size_t)off, (size_t)n, d_done, (size_t)len, (size_t)len, (size_t)T,
+                                   cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = (int)e;
+    bit_words_before += words;
+    (void)osz; (void)rsz;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e = cudaStreamSynchronize(v->streams[i]);
+    if (e != cudaSuccess && rc == 0) rc = (int)e;
+  }
+  if (rc == 0) {   // a failed call leaves the step counter (and fishing-v10's drifting r) where they were
+    v->step_idx += (uint64_t)T;
+    v->p.r = r_after;
   }
   return rc;
 }
@@ -645,133 +829,54 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
                           double* reward_out, uint8_t* done_out) {
   if (!v || !actions || !obs_out || !reward_out || !done_out || T < 0) return FISHING_E_ARG;
   if (!v->was_reset) return FISHING_E_STATE;
-  const int asz = act_size(action_dtype);
-  if (!asz) return FISHING_E_ARG;
-  if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
-  cudaError_t e = cudaSetDevice(v->device);
-  if (e != cudaSuccess) return (int)e;
-  // Zero-copy mode: when every host array is page-locked (fishing_host_alloc / cudaHostRegister) the kernel reads the
-  // actions and writes observations / rewards / dones straight over PCIe, one launch per lock-step with programmatic
-  // dependent launch between them -- no staging copies, no copy-engine round trips.
-  {
+  // Zero-copy mode (opt-in, FISHING_VEC_ZEROCOPY=1): when every host array is page-locked the kernel reads the actions and
+  // writes observations / rewards / dones straight over PCIe, one launch per lock-step -- no staging, no copy engines.
+  if (zero_copy_enabled()) {
+    const int asz = act_size(action_dtype);
+    if (!asz) return FISHING_E_ARG;
+    if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
     void* d_act = device_alias(actions);
     void* d_obs = device_alias(obs_out);
     void* d_rew = device_alias(reward_out);
     void* d_done = device_alias(done_out);
-    if (d_act && d_obs && d_rew && d_done && zero_copy_enabled()) {
+    if (d_act && d_obs && d_rew && d_done) {
+      cudaError_t e = cudaSetDevice(v->device);
+      if (e != cudaSuccess) return (int)e;
       cudaStream_t st = v->streams[0];
       fishing_params q = v->p;
       int rc = 0;
       for (int64_t t = 0; t < T && rc == 0; ++t) {
         q.flags = (v->p.flags & ~(uint32_t)FISHING_PDL) | (t > 0 ? (uint32_t)FISHING_PDL : 0u);
-        rc = step_impl(&q, v->n, v->env_id0, v->step_idx, static_cast<const char*>(d_act) + t * v->n * asz, action_dtype, nullptr,
-                       nullptr, v->soa, v->soa.state, static_cast<double*>(d_rew) + t * v->n,
+        rc = step_impl(&q, v->n, v->env_id0, v->step_idx + (uint64_t)t, static_cast<const char*>(d_act) + t * v->n * asz,
+                       action_dtype, nullptr, nullptr, v->soa, v->soa.state, static_cast<double*>(d_rew) + t * v->n,
                        static_cast<uint8_t*>(d_done) + t * v->n, v->d_terminal, nullptr, nullptr,
                        static_cast<double*>(d_obs) + t * v->n, st);
-        v->step_idx += 1;
         if (q.kind == FISHING_V10) {
           volatile double r_next = q.r + q.alpha;
           q.r = r_next;
-          v->p.r = r_next;
         }
       }
       e = cudaStreamSynchronize(st);
-      return rc ? rc : (int)e;
+      if (rc == 0 && e != cudaSuccess) rc = (int)e;
+      if (rc == 0) {
+        v->step_idx += (uint64_t)T;
+        v->p.r = q.r;
+      }
+      return rc;
     }
   }
-  // a fixed chunk -> stream assignment keeps every dependency (state, staging buffers) inside one in-order stream;
-  // the three streams keep an H2D, a kernel and a D2H of different chunks in flight at the same time
-  const int64_t n = v->n;
-  int64_t chunk = ((n + 2) / 3 + 1023) / 1024 * 1024;
-  if (chunk > n) chunk = n;
-  int rc = 0;
-  for (int64_t t = 0; t < T && rc == 0; ++t) {
-    int k = 0;
-    for (int64_t off = 0; off < n && rc == 0; off += chunk, ++k) {
-      const int64_t len = (n - off < chunk) ? n - off : chunk;
-      cudaStream_t st = v->streams[k % 3];
-      char* d_act = static_cast<char*>(v->d_action) + off * asz;
-      e = cudaMemcpyAsync(d_act, static_cast<const char*>(actions) + (t * n + off) * asz, (size_t)len * asz,
-                          cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) { rc = (int)e; break; }
-      fishing_soa s = v->soa;
-      s.state += off; s.years += off;
-      if (s.K_env) { s.K_env += off; s.r_env += off; }
-      if (s.model) s.model += off;
-      rc = fishing_step(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, nullptr, nullptr, s, v->d_obs + off,
-                        v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, st);
-      if (rc) break;
-      e = cudaMemcpyAsync(obs_out + t * n + off, v->d_obs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(reward_out + t * n + off, v->d_reward + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(done_out + t * n + off, v->d_done + off, (size_t)len, cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-    v->step_idx += 1;
-    if (v->p.kind == FISHING_V10) {
-      volatile double r_next = v->p.r + v->p.alpha;
-      v->p.r = r_next;
-    }
-  }
-  for (int i = 0; i < 3; ++i) {
-    e = cudaStreamSynchronize(v->streams[i]);
-    if (e != cudaSuccess && rc == 0) rc = (int)e;
-  }
-  return rc;
+  return vec_step_many_core(v, T, actions, action_dtype, obs_out, reward_out, done_out, 0u);
 }
 
 int fishing_vec_step_many_f32(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, float* obs_out,
                               float* reward_out, uint8_t* done_out) {
-  if (!v || !actions || !obs_out || !reward_out || !done_out || T < 0) return FISHING_E_ARG;
-  if (!v->was_reset) return FISHING_E_STATE;
-  const int asz = act_size(action_dtype);
-  if (!asz) return FISHING_E_ARG;
-  if (!act_matches_kind(v->p.kind, action_dtype)) return FISHING_E_KIND;
-  cudaError_t e = cudaSetDevice(v->device);
-  if (e != cudaSuccess) return (int)e;
-  const int64_t n = v->n;
-  if (!v->d_obs32) {
-    if (cudaMalloc(&v->d_obs32, (size_t)n * 4) != cudaSuccess || cudaMalloc(&v->d_reward32, (size_t)n * 4) != cudaSuccess)
-      return (int)cudaErrorMemoryAllocation;
-  }
-  int64_t chunk = ((n + 2) / 3 + 1023) / 1024 * 1024;
-  if (chunk > n) chunk = n;
-  int rc = 0;
-  for (int64_t t = 0; t < T && rc == 0; ++t) {
-    int k = 0;
-    for (int64_t off = 0; off < n && rc == 0; off += chunk, ++k) {
-      const int64_t len = (n - off < chunk) ? n - off : chunk;
-      cudaStream_t st = v->streams[k % 3];
-      char* d_act = static_cast<char*>(v->d_action) + off * asz;
-      e = cudaMemcpyAsync(d_act, static_cast<const char*>(actions) + (t * n + off) * asz, (size_t)len * asz,
-                          cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) { rc = (int)e; break; }
-      fishing_soa s = v->soa;
-      s.state += off; s.years += off;
-      if (s.K_env) { s.K_env += off; s.r_env += off; }
-      if (s.model) s.model += off;
-      rc = step_impl(&v->p, len, v->env_id0 + off, v->step_idx, d_act, action_dtype, nullptr, nullptr, s, v->d_obs + off,
-                     v->d_reward + off, v->d_done + off, v->d_terminal + off, nullptr, nullptr, nullptr, st);
-      if (rc) break;
-      rc = (int)launch_cast_f32(v->d_obs + off, v->d_reward + off, v->d_obs32 + off, v->d_reward32 + off, len, st);
-      if (rc) break;
-      e = cudaMemcpyAsync(obs_out + t * n + off, v->d_obs32 + off, (size_t)len * 4, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(reward_out + t * n + off, v->d_reward32 + off, (size_t)len * 4, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(done_out + t * n + off, v->d_done + off, (size_t)len, cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-    v->step_idx += 1;
-    if (v->p.kind == FISHING_V10) {
-      volatile double r_next = v->p.r + v->p.alpha;
-      v->p.r = r_next;
-    }
-  }
-  for (int i = 0; i < 3; ++i) {
-    e = cudaStreamSynchronize(v->streams[i]);
-    if (e != cudaSuccess && rc == 0) rc = (int)e;
-  }
-  return rc;
+  return vec_step_many_core(v, T, actions, action_dtype, obs_out, reward_out, done_out,
+                            FISHING_WIRE_OBS_F32 | FISHING_WIRE_REWARD_F32);
+}
+
+int fishing_vec_step_many_wire(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, void* obs_out,
+                               void* reward_out, void* done_out, uint32_t wire) {
+  return vec_step_many_core(v, T, actions, action_dtype, obs_out, reward_out, done_out, wire);
 }
 
 int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out) {
@@ -781,6 +886,50 @@ int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out) {
   e = cudaMemcpyAsync(terminal_out, v->d_terminal, (size_t)v->n * sizeof(double), cudaMemcpyDeviceToHost, v->streams[0]);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaStreamSynchronize(v->streams[0]);
+}
+
+// which: 0 state f64, 1 years i32, 2 K_env f64, 3 r_env f64, 4 model i32, 5 terminal observations f64
+static int vec_array(fishing_vec* v, int32_t which, void** ptr, size_t* elem) {
+  switch (which) {
+    case FISHING_ARRAY_STATE: *ptr = v->soa.state; *elem = 8; break;
+    case FISHING_ARRAY_YEARS: *ptr = v->soa.years; *elem = 4; break;
+    case FISHING_ARRAY_K: *ptr = v->soa.K_env; *elem = 8; break;
+    case FISHING_ARRAY_R: *ptr = v->soa.r_env; *elem = 8; break;
+    case FISHING_ARRAY_MODEL: *ptr = v->soa.model; *elem = 4; break;
+    case FISHING_ARRAY_TERMINAL: *ptr = v->d_terminal; *elem = 8; break;
+    default: return FISHING_E_ARG;
+  }
+  return *ptr ? 0 : FISHING_E_KIND;   // the environment id has no such array (K / r: fishing-v4, model: fishing-v11)
+}
+
+int fishing_vec_fetch_array(fishing_vec* v, int32_t which, void* out) {
+  if (!v || !out) return FISHING_E_ARG;
+  void* src; size_t elem;
+  if (int rc = vec_array(v, which, &src, &elem)) return rc;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(out, src, (size_t)v->n * elem, cudaMemcpyDeviceToHost, v->streams[0]);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(v->streams[0]);
+}
+
+int fishing_vec_store_array(fishing_vec* v, int32_t which, const void* in) {
+  if (!v || !in) return FISHING_E_ARG;
+  if (which == FISHING_ARRAY_TERMINAL) return FISHING_E_ARG;
+  void* dst; size_t elem;
+  if (int rc = vec_array(v, which, &dst, &elem)) return rc;
+  cudaError_t e = cudaSetDevice(v->device);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(dst, in, (size_t)v->n * elem, cudaMemcpyHostToDevice, v->streams[0]);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(v->streams[0]);
+}
+
+int fishing_vec_set_params(fishing_vec* v, const fishing_params* p) {
+  if (!v || !p) return FISHING_E_ARG;
+  if (p->kind != v->p.kind) return FISHING_E_KIND;     // the arrays of the handle belong to its environment id
+  v->p = *p;
+  return 0;
 }
 
 int fishing_host_alloc(void** ptr, int64_t bytes) {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/fishing_b200.h"
+#include "philox.cuh"   // GlobalTabs / exp_tab (csrc/normal.cuh)
 
 namespace fishing {
 
@@ -147,9 +148,9 @@ __device__ __forceinline__ double action_discrete(double q, double n_actions, do
 }
 
 // population_draw: base_fishing_env.py:121-133 (logistic) / fishing_tipping_env.py:24-35 (tipping point)
-template <int GROWTH, int PM>
+template <int GROWTH, int PM, class Tabs = GlobalTabs>
 __device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy,
-                                       const KDiv& kd = KDiv()) {
+                                       const KDiv& kd = KDiv(), const Tabs& tb = Tabs()) {
   const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, K, kd) : div_z(x1, K));
   const double room = __dsub_rn(1.0, frac);
   if (GROWTH == LOGISTIC) {
@@ -165,7 +166,7 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
     double e = __dmul_rn(__dmul_rn(r, room), __dsub_rn(x1, C));
     if (noisy) e = __dadd_rn(e, __dmul_rn(__dmul_rn(x1, sigma), z));
     else if (PM == P_PERENV || kd.odd) e = __dadd_rn(e, __dmul_rn(x1, 0.0));
-    return np_max0(__dmul_rn(x1, exp(e)));
+    return np_max0(__dmul_rn(x1, exp_tab(e, tb)));
   }
 }
 

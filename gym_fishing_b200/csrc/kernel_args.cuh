@@ -40,6 +40,16 @@ struct StepArgs {
   double* __restrict__ out_harvest;  // optional: harvest (un-clipped reward)
   double* __restrict__ out_obs2;     // optional second copy of the observations (zero-copy host front end: out_obs is
                                      // the device state, out_obs2 a device-mapped pinned host array)
+  // VecMonitor-style episode statistics (optional, all three or none; fishing_step_ex): the running return of the current
+  // episode, and the return / length of the last finished one, rolled over in the step that ends it
+  double* ep_return;
+  double* __restrict__ last_ep_return;
+  int32_t* __restrict__ last_ep_length;
+  // optional float32 copies of observations / rewards (what a stable-baselines3 VecEnv hands to the learner)
+  float* __restrict__ out_obs32;
+  float* __restrict__ out_reward32;
+  // optional bit-packed copy of out_done: bit (i & 63) of word (i >> 6) = done of environment i (vector path only)
+  unsigned long long* __restrict__ out_done_bits;
   // log-normal family (fishing-v5..v11)
   GrowthP gp;
   int32_t derive_on_device;          // fishing-v10: recompute gp's derived fields with the device's log (like K2 does)
@@ -106,7 +116,6 @@ cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r
                           double z, void* out, cudaStream_t st);
 cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
                              cudaStream_t st);
-cudaError_t launch_cast_f32(const double* a, const double* b, float* a32, float* b32, int64_t n, cudaStream_t st);
 cudaError_t launch_fp64_probe(double* scratch, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);

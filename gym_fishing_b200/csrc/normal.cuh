@@ -33,6 +33,8 @@
 #else
 #include <cmath>
 #include <cstring>
+using std::exp;
+using std::fabs;
 #define FN_HD inline
 struct double2 { double x, y; };
 #endif
@@ -130,14 +132,20 @@ FN_HD double i2d(int e) {
 struct NormalTables {
   double2 log_e[FISHING_NLOG + 1];
   double2 trig_e[FISHING_NTRIG + 1];
+  double exp_e[64];                    // 2^(j/64), for exp_tab() below
 };
-static __device__ const NormalTables g_normal_tables = {FISHING_LOG_TABLE_INIT, FISHING_TRIG_TABLE_INIT};
+static __device__ const NormalTables g_normal_tables = {FISHING_LOG_TABLE_INIT, FISHING_TRIG_TABLE_INIT, FISHING_EXP_TABLE_INIT};
 // polynomial coefficients: from the constant bank the compiler loads them in pairs into uniform registers
-static __constant__ double FN_C[11] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
-                                       FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0};
+static __constant__ double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
+                                       FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0,
+                                       FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
+                                       FISHING_PE2, FISHING_PE1, FISHING_PE0};
 #define FN_COEF(k) FN_C[k]
 
 struct GlobalTabs {
+  __device__ __forceinline__ double exp_at(uint32_t byte_off) const {
+    return __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(g_normal_tables.exp_e) + byte_off));
+  }
   __device__ __forceinline__ double2 log_at(uint32_t byte_off) const {
     return __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const char*>(g_normal_tables.log_e) + byte_off));
   }
@@ -150,10 +158,12 @@ struct GlobalTabs {
 struct SharedTabs {
   const char* lt;
   const char* tt;
+  const char* et;
+  __device__ __forceinline__ double exp_at(uint32_t byte_off) const { return *reinterpret_cast<const double*>(et + byte_off); }
   __device__ __forceinline__ double2 log_at(uint32_t byte_off) const { return *reinterpret_cast<const double2*>(lt + byte_off); }
   __device__ __forceinline__ double2 trig_at(uint32_t byte_off) const { return *reinterpret_cast<const double2*>(tt + byte_off); }
 };
-constexpr int NORMAL_TABLE_ENTRIES = FISHING_NLOG + 1 + FISHING_NTRIG + 1;
+constexpr int NORMAL_TABLE_ENTRIES = FISHING_NLOG + 1 + FISHING_NTRIG + 1 + 32;   // in double2 units; the last 32 = exp_e[64]
 // `buf`: NORMAL_TABLE_ENTRIES double2 of shared memory; called by all BS threads of the block.  Contains a __syncthreads().
 template <int BS>
 __device__ __forceinline__ SharedTabs stage_normal_tables(double2* buf) {
@@ -167,15 +177,20 @@ __device__ __forceinline__ SharedTabs stage_normal_tables(double2* buf) {
   SharedTabs t;
   t.lt = reinterpret_cast<const char*>(buf);
   t.tt = reinterpret_cast<const char*>(buf + FISHING_NLOG + 1);
+  t.et = reinterpret_cast<const char*>(buf + FISHING_NLOG + 1 + FISHING_NTRIG + 1);
   return t;
 }
 #else
 static const double2 h_normal_log_table[FISHING_NLOG + 1] = FISHING_LOG_TABLE_INIT;
 static const double2 h_normal_trig_table[FISHING_NTRIG + 1] = FISHING_TRIG_TABLE_INIT;
-static const double FN_C[11] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
-                                FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0};
+static const double h_exp_table[64] = FISHING_EXP_TABLE_INIT;
+static const double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
+                                FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0,
+                                FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
+                                FISHING_PE2, FISHING_PE1, FISHING_PE0};
 #define FN_COEF(k) FN_C[k]
 struct HostTabs {
+  double exp_at(uint32_t byte_off) const { return h_exp_table[byte_off >> 3]; }
   double2 log_at(uint32_t byte_off) const { return h_normal_log_table[byte_off >> 4]; }
   double2 trig_at(uint32_t byte_off) const { return h_normal_trig_table[byte_off >> 4]; }
 };
@@ -221,6 +236,39 @@ FN_HD Normal2 normal_from_words(const uint32_t (&w)[4], const Tabs& tb) {
   out.z0 = fma_(-RS, sth, fma_(RC, cm1, RC));
   out.z1 = fma_(RC, sth, fma_(RS, cm1, RS));
   return out;
+}
+
+// exp(x) for the tipping-point growth of fishing-v2 (fishing_tipping_env.py:31: x1 * exp(...)), table-assisted like the
+// pieces above: x = k ln2/64 + r with k = round(64 x / ln 2) read from the low bits of x * 64/ln2 + 1.5 * 2^52,
+// exp(x) = 2^(k >> 6) * 2^((k & 63)/64) * (1 + r + r^2 P(r)), |r| <= ln2/128, P a cubic (abs. error 2^-57.7).  10 FP64
+// instructions and one 8-byte table load against libdevice's ~20 plus two dozen immediates rebuilt every call; mean 0.33,
+// worst 1.02 ulp (tools/normal_accuracy.cpp).  The reference computes this with numpy's exp, itself not correctly rounded: fishing-v2
+// parity is a 1e-12 tolerance either way.  Beyond |x| = 700 the scaling is done by two multiplications
+// (overflow to inf, gradual underflow to 0); infinities and NaN are patched in a branch that is practically never taken.
+template <class Tabs>
+FN_HD double exp_tab(double x, const Tabs& tb) {
+  using namespace nrm;
+#ifdef FISHING_AB_LIBEXP
+  return exp(x);      // A/B timing build: the library routine
+#endif
+  const double kf = fma_(x, FN_COEF(11), 0x1.8p52);
+  const int ki = (int)lo32(kf);
+  const double kd = sub(kf, 0x1.8p52);
+  double r = fma_(kd, FN_COEF(12), x);
+  r = fma_(kd, FN_COEF(13), r);
+  const double r2 = mul(r, r);
+  double p = fma_(FN_COEF(14), r, FN_COEF(15));
+  p = fma_(p, r, FN_COEF(16));
+  p = fma_(p, r, FN_COEF(17));
+  const double q = fma_(r2, p, r);                                  // exp(r) - 1
+  const double T = tb.exp_at(((uint32_t)ki & 63u) << 3);
+  const double y = fma_(T, q, T);                                   // in (0.99, 2): a normal number
+  const int m = ki >> 6;
+  if (fabs(x) < 700.0) return hilo(hi32(y) + (uint32_t)(m << 20), lo32(y));   // times 2^m: the result stays normal
+  // rare: results that overflow, underflow or are subnormal; infinities and NaN (for which everything above is garbage)
+  if (!(fabs(x) <= 1400.0)) return x != x ? add(x, x) : (x > 0.0 ? hilo(0x7FF00000u, 0u) : 0.0);
+  const int m1 = m >> 1, m2 = m - m1;                               // two normal powers of two: |m| < 2048
+  return mul(mul(y, hilo((uint32_t)(m1 + 1023) << 20, 0u)), hilo((uint32_t)(m2 + 1023) << 20, 0u));
 }
 
 }  // namespace fishing

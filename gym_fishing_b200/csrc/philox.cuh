@@ -107,6 +107,8 @@ __device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uin
 #include "normal_v1.cuh"
 struct GlobalTabs {};
 struct SharedTabs {};
+template <class Tabs>
+__device__ __forceinline__ double exp_tab(double x, const Tabs&) { return exp(x); }
 constexpr int NORMAL_TABLE_ENTRIES = 1;
 template <int BS>
 __device__ __forceinline__ SharedTabs stage_normal_tables(double2*) { return SharedTabs(); }

@@ -348,7 +348,7 @@ enum : int { M_PLAIN = 0, M_AUTO_RESET = 1, M_FREEZE = 2 };
 
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
-                                              uint64_t gid, double& reward_out, bool& done_out) {
+                                              uint64_t gid, const SharedTabs& tb, double& reward_out, bool& done_out) {
   constexpr bool auto_reset = MODE == M_AUTO_RESET, freeze = MODE == M_FREEZE;
   double x = __dadd_rn(e.s, 1.0);
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
@@ -377,7 +377,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
     double ex = __dmul_rn(__dmul_rn(e.r, room), __dsub_rn(x1, a.C));
     if (NOISY) ex = __dadd_rn(ex, __dmul_rn(__dmul_rn(x1, a.sigma), z));
     else if (PM == P_PERENV) ex = __dadd_rn(ex, __dmul_rn(x1, 0.0));
-    g = __dmul_rn(x1, exp(ex));
+    g = __dmul_rn(x1, exp_tab(ex, tb));
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
   const double x2 = alive ? g : 0.0;
@@ -414,10 +414,10 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
 
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
-                                              uint64_t gid) {
+                                              uint64_t gid, const SharedTabs& tb) {
   double reward;
   bool done;
-  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e, action, z, t, gid, reward, done);
+  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e, action, z, t, gid, tb, reward, done);
 }
 
 // the return to report: all episodes (auto-reset), or the first one (frozen environments stop accumulating by themselves)
@@ -431,9 +431,10 @@ __device__ __forceinline__ double fast_env_return(const FastEnv& e) {
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
 __global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel(const RolloutArgs a) {
   // the Box-Muller tables, staged once per block for the T draws of every thread (normal.cuh)
-  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
+  __shared__ double2 s_tab[TABLES ? NORMAL_TABLE_ENTRIES : 1];
   SharedTabs tb = {};
-  if (NOISY) tb = stage_normal_tables<128>(s_tab);
+  if (TABLES) tb = stage_normal_tables<128>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
   Lanes L;
@@ -499,14 +500,14 @@ __global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel
       z0 = d.z0; z1 = d.z1;
     }
     if (MODE == M_FREEZE) {
-      if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0);
-      if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1);
+      if (!e0.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, tb);
+      if (!e1.frozen) fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, tb);
       return e0.frozen && e1.frozen;
     } else if (TRACE) {
       double r0, r1;
       bool d0, d1;
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, r0, d0);
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, r1, d1);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, tb, r0, d0);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, tb, r1, d1);
       // adjacent-pair layout and all three rows present (launch_rollout_p checks both): one 16-byte / 16-byte / 2-byte
       // streaming store each through pointers that advance by one row per step
       __stcs(reinterpret_cast<double2*>(tr_obs), make_double2(e0.s, e1.s));
@@ -516,8 +517,8 @@ __global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel
       tr_rew += row_f64;
       tr_done += row_u8;
     } else {
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0);
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, tb);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, tb);
     }
     return false;
   };
@@ -549,9 +550,10 @@ __global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel
 // are strided by m/LV so that neighbouring threads touch neighbouring addresses.
 template <int GROWTH, int PM, bool NOISY, int LV, int MODE>
 __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a) {
-  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
+  __shared__ double2 s_tab[TABLES ? NORMAL_TABLE_ENTRIES : 1];
   SharedTabs tb = {};
-  if (NOISY) tb = stage_normal_tables<128>(s_tab);
+  if (TABLES) tb = stage_normal_tables<128>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = a.noise_id_div, mq = m / LV;
   if (tid >= (a.n >> 1) / LV) return;
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
     for (int k = 0; k < 2 * LV; ++k) {
       if (MODE != M_FREEZE || !e[k].frozen)
         fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, SAFE>(a, e[k], 0.0, z[k & 1], t,
-                                                                                 (uint64_t)(a.env_id0 + idx[k]));
+                                                                                 (uint64_t)(a.env_id0 + idx[k]), tb);
       all_frozen = all_frozen && e[k].frozen;
     }
     return all_frozen;
@@ -642,9 +644,10 @@ static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_
 // body is the noise-free dynamics plus four SHFL, at the register count -- and occupancy -- of the plain kernel.
 template <int GROWTH, int PM, bool NOISY, int MODE>
 __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutArgs a) {
-  __shared__ double2 s_tab[NOISY ? NORMAL_TABLE_ENTRIES : 1];
+  constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
+  __shared__ double2 s_tab[TABLES ? NORMAL_TABLE_ENTRIES : 1];
   SharedTabs tb = {};
-  if (NOISY) tb = stage_normal_tables<128>(s_tab);
+  if (TABLES) tb = stage_normal_tables<128>(s_tab);
   const unsigned full = 0xffffffffu;
   const int64_t m = a.noise_id_div;                      // levels, a multiple of 32
   const int64_t warps_per_pair = m >> 5;
@@ -671,11 +674,11 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
     d.z0 = d.z1 = 0.0;
     if (NOISY) d = normal_pair_keys(a.keys, noise_pair, a.step0, FISHING_STREAM_STEP, tb);
     if (__any_sync(full, unsafe)) {
-      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e0, 0.0, d.z0, 0, gid0);
-      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e1, 0.0, d.z1, 0, gid1);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e0, 0.0, d.z0, 0, gid0, tb);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE, true>(a, e1, 0.0, d.z1, 0, gid1, tb);
     } else {
-      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, d.z0, 0, gid0);
-      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, d.z1, 0, gid1);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, d.z0, 0, gid0, tb);
+      fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, d.z1, 0, gid1, tb);
     }
     all_done = MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen);
   }
@@ -695,9 +698,9 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
       }
       const int t = t0 + dt;
       if (MODE != M_FREEZE || !e0.frozen)
-        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, z0, t, gid0);
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, z0, t, gid0, tb);
       if (MODE != M_FREEZE || !e1.frozen)
-        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, z1, t, gid1);
+        fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, z1, t, gid1, tb);
       if (MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen)) {   // warp-uniform: the shuffles need every lane
         all_done = true;
         break;
@@ -824,23 +827,25 @@ cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStrea
 constexpr int REDUCE_ROWS = 64;
 
 __global__ void __launch_bounds__(256) reduce_pass1(const double* __restrict__ ret, const int32_t* __restrict__ done_step,
-                                                     int64_t rows, int64_t groups, double* __restrict__ partial) {
+                                                     int64_t rows, int64_t groups, int64_t chunks, double* __restrict__ partial) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t chunk = blockIdx.y;
   if (g >= groups) return;
-  const int64_t r0 = chunk * REDUCE_ROWS;
-  const int64_t r1 = (r0 + REDUCE_ROWS < rows) ? r0 + REDUCE_ROWS : rows;
-  double s = 0.0, s2 = 0.0, nd = 0.0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const double v = ret[r * groups + g];
-    s = __dadd_rn(s, v);
-    s2 = __dadd_rn(s2, __dmul_rn(v, v));
-    if (done_step && done_step[r * groups + g] >= 0) nd += 1.0;
+  // blockIdx.y strides over the chunks (gridDim.y is capped at 65535; more than 4.19 million rows need several rounds)
+  for (int64_t chunk = blockIdx.y; chunk < chunks; chunk += gridDim.y) {
+    const int64_t r0 = chunk * REDUCE_ROWS;
+    const int64_t r1 = (r0 + REDUCE_ROWS < rows) ? r0 + REDUCE_ROWS : rows;
+    double s = 0.0, s2 = 0.0, nd = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const double v = ret[r * groups + g];
+      s = __dadd_rn(s, v);
+      s2 = __dadd_rn(s2, __dmul_rn(v, v));
+      if (done_step && done_step[r * groups + g] >= 0) nd += 1.0;
+    }
+    double* p = partial + (chunk * groups + g) * 3;
+    p[0] = s;
+    p[1] = s2;
+    p[2] = nd;
   }
-  double* p = partial + (chunk * groups + g) * 3;
-  p[0] = s;
-  p[1] = s2;
-  p[2] = nd;
 }
 
 __global__ void __launch_bounds__(256) reduce_pass2(double* __restrict__ partial, int64_t chunks, int64_t groups,
@@ -911,9 +916,8 @@ cudaError_t launch_reduce(const double* ret, const int32_t* done_step, int64_t n
   const int64_t vg = virtual_groups(n, groups);
   const int64_t rows = n / vg;
   const int64_t chunks = reduce_chunks(n, groups);
-  if (chunks > 65535) return cudaErrorInvalidConfiguration;
-  dim3 grid((unsigned)((vg + 255) / 256), (unsigned)chunks);
-  reduce_pass1<<<grid, 256, 0, st>>>(ret, done_step, rows, vg, scratch);
+  dim3 grid((unsigned)((vg + 255) / 256), (unsigned)(chunks < 65535 ? chunks : 65535));
+  reduce_pass1<<<grid, 256, 0, st>>>(ret, done_step, rows, vg, chunks, scratch);
   count_launch();
   double* cols = vg == groups ? out : scratch + chunks * vg * 3;
   reduce_pass2<<<(unsigned)((vg + 255) / 256), 256, 0, st>>>(scratch, chunks, vg, cols);

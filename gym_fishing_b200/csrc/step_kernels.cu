@@ -89,7 +89,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // pair, in a kernel that is bound by instruction issue -- are compiled out (cfg 2: 6.83 -> 6.53 us per launch).  The
 // rollout-buffer loop of bench.py and FishingVecEnv's torch path run this instantiation.  The lean fishing-v4 kernel is
 // held to 48 registers (5 resident blocks per SM instead of 4; 36 bytes of spill): 6.78 -> 6.57 ms per 128 steps of cfg 4.
-template <int GROWTH, int PM, int ACT, int BS = 128, bool LEAN = false>
+// EXTRA (never together with LEAN) = the instantiation that also keeps the VecMonitor statistics and writes float32 copies of
+// observations / rewards (fishing_step_ex): a kernel of its own, so that neither the lean nor the plain instantiation pays
+// registers for it.
+template <int GROWTH, int PM, int ACT, int BS = 128, bool LEAN = false, bool EXTRA = false>
 __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 : 0) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
@@ -144,8 +147,9 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
   }
 #endif
   if (a.flags & STEP_FLAG_PDL) pdl_wait();
-  // the fishing-v4 kernel keeps idle lanes alive: every warp of the block has to sign off at the end (reset job list)
-  if (!live && PM != P_PERENV) return;
+  // the fishing-v4 kernel keeps idle lanes alive: every warp of the block has to sign off at the end (reset job list); so
+  // does the EXTRA instantiation (its done-bit packing is a full-warp ballot)
+  if (!live && PM != P_PERENV && !EXTRA) return;
 
   // ---- phase B: state written by the previous launch
   double2 s = make_double2(0.0, 0.0);
@@ -177,6 +181,18 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
     reinterpret_cast<int2*>(a.years)[j] = make_int2(e0.years, e1.years);
     if (!LEAN && a.out_stock) reinterpret_cast<double2*>(a.out_stock)[j] = make_double2(e0.stock, e1.stock);
     if (!LEAN && a.out_harvest) reinterpret_cast<double2*>(a.out_harvest)[j] = make_double2(e0.harvest, e1.harvest);
+    if (EXTRA) {
+      if (a.ep_return) {
+        double2 acc = reinterpret_cast<const double2*>(a.ep_return)[j];
+        acc.x = __dadd_rn(acc.x, e0.reward);
+        acc.y = __dadd_rn(acc.y, e1.reward);
+        if (e0.done) { a.last_ep_return[i0] = acc.x; a.last_ep_length[i0] = yr.x + 1; acc.x = 0.0; }
+        if (e1.done) { a.last_ep_return[i0 + 1] = acc.y; a.last_ep_length[i0 + 1] = yr.y + 1; acc.y = 0.0; }
+        reinterpret_cast<double2*>(a.ep_return)[j] = acc;
+      }
+      if (a.out_obs32) st_stream(reinterpret_cast<float2*>(a.out_obs32) + j, make_float2((float)e0.obs, (float)e1.obs));
+      if (a.out_reward32) st_stream(reinterpret_cast<float2*>(a.out_reward32) + j, make_float2((float)e0.reward, (float)e1.reward));
+    }
     if (e0.reset_fired | e1.reset_fired) {
       if (!LEAN && a.out_terminal) {
         if (e0.reset_fired) a.out_terminal[i0] = e0.terminal;
@@ -187,6 +203,23 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
         reinterpret_cast<double2*>(a.r_env)[j] = make_double2(e0.r, e1.r);
       }
       if (GROWTH == G_MODEL) reinterpret_cast<int2*>(a.model)[j] = make_int2(e0.model, e1.model);
+    }
+  }
+  if (EXTRA && a.out_done_bits) {
+    // 64 environments per warp -> one 64-bit word: even environments from one ballot, odd ones from the other, interleaved
+    const unsigned full = 0xffffffffu;
+    const unsigned m0 = __ballot_sync(full, live && e0.done), m1 = __ballot_sync(full, live && e1.done);
+    if ((threadIdx.x & 31) == 0 && live) {
+      auto spread = [](unsigned m) {
+        unsigned long long x = m;
+        x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+        x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+        x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+        x = (x | (x << 2)) & 0x3333333333333333ull;
+        x = (x | (x << 1)) & 0x5555555555555555ull;
+        return x;
+      };
+      a.out_done_bits[j >> 5] = spread(m0) | (spread(m1) << 1);
     }
   }
   if (deferred) {
@@ -252,9 +285,17 @@ __global__ void __launch_bounds__(256) step_kernel_scalar(const StepArgs a) {
     if (a.out_obs2) a.out_obs2[i] = e.obs;
     a.out_reward[i] = e.reward;
     a.out_done[i] = e.done;
+    const int32_t years_in = a.years[i];
     a.years[i] = e.years;
     if (a.out_stock) a.out_stock[i] = e.stock;
     if (a.out_harvest) a.out_harvest[i] = e.harvest;
+    if (a.ep_return) {
+      double acc = __dadd_rn(a.ep_return[i], e.reward);
+      if (e.done) { a.last_ep_return[i] = acc; a.last_ep_length[i] = years_in + 1; acc = 0.0; }
+      a.ep_return[i] = acc;
+    }
+    if (a.out_obs32) a.out_obs32[i] = (float)e.obs;
+    if (a.out_reward32) a.out_reward32[i] = (float)e.reward;
     if (e.reset_fired) {
       if (a.out_terminal) a.out_terminal[i] = e.terminal;
       if (PM == P_PERENV) {
@@ -451,7 +492,8 @@ static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
 template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
   constexpr bool CAN_LEAN = true;
-  const bool lean = CAN_LEAN && !a.noise && !a.reset_noise && !a.out_obs2 && !a.out_stock && !a.out_harvest && !a.out_terminal;
+  const bool extra = a.ep_return || a.out_obs32 || a.out_reward32 || a.out_done_bits;
+  const bool lean = CAN_LEAN && !extra && !a.noise && !a.reset_noise && !a.out_obs2 && !a.out_stock && !a.out_harvest && !a.out_terminal;
   if (vec) {
     const int64_t npairs = a.n >> 1;
     const int64_t blocks = (npairs + 255) / 256;
@@ -470,9 +512,11 @@ static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
       cfg.numAttrs = 1;
       count_launch();
       if (lean) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, CAN_LEAN>, a);
+      if (extra) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, false, true>, a);
       return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, false>, a);
     }
     if (lean) step_kernel_vec2<GROWTH, PM, ACT, 256, CAN_LEAN><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else if (extra) step_kernel_vec2<GROWTH, PM, ACT, 256, false, true><<<(unsigned)blocks, 256, 0, st>>>(a);
     else step_kernel_vec2<GROWTH, PM, ACT, 256, false><<<(unsigned)blocks, 256, 0, st>>>(a);
   } else {
     const int grid = grid_for(a.n, 256, 8);
@@ -549,23 +593,6 @@ cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r
   const int grid = grid_for(n, 256, 8);
   if (f32) growth_kernel<float><<<grid, 256, 0, st>>>(kind, n, (const float*)x, r, K, C, sigma, z, (float*)out);
   else growth_kernel<double><<<grid, 256, 0, st>>>(kind, n, (const double*)x, r, K, C, sigma, z, (double*)out);
-  count_launch();
-  return cudaGetLastError();
-}
-
-// float32 copies of two float64 arrays (the stable-baselines3-dtype host front end).  Kept OUT of the step kernel on purpose:
-// two more optional outputs there cost 6 registers = one resident block per SM = 9 % of the headline throughput.
-__global__ void __launch_bounds__(256) cast_f32_kernel(const double* __restrict__ a, const double* __restrict__ b,
-                                                        float* __restrict__ a32, float* __restrict__ b32, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    a32[i] = (float)a[i];
-    b32[i] = (float)b[i];
-  }
-}
-
-cudaError_t launch_cast_f32(const double* a, const double* b, float* a32, float* b32, int64_t n, cudaStream_t st) {
-  cast_f32_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(a, b, a32, b32, n);
   count_launch();
   return cudaGetLastError();
 }

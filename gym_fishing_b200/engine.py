@@ -143,6 +143,9 @@ class EnvBatch:
             _chk_dev(reset_model, "reset_model", torch.int32, self.n)
             if mask is not None:
                 mask = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+                _chk_dev(mask, "mask", torch.uint8, self.n)
+            if out_obs is not None:
+                _chk_dev(out_obs, "out_obs", torch.float64, self.n)
             p = self.params()
             with torch.cuda.device(self.device):
                 rc = nat.lib().fishing_reset_models(ct.byref(p), self.n, self.env_id0, self.epoch, _ptr(mask),
@@ -191,6 +194,13 @@ class EnvBatch:
             _chk_dev(reset_noise, "reset_noise", torch.float64, 2 * self.n)
         if out_terminal is not None:
             _chk_dev(out_terminal, "out_terminal", torch.float64, self.n)
+        # the optional arrays reach the kernel as raw pointers too: same device / dtype / length checks
+        if out_stock is not None:
+            _chk_dev(out_stock, "out_stock", torch.float64, self.n)
+        if out_harvest is not None:
+            _chk_dev(out_harvest, "out_harvest", torch.float64, self.n)
+        if state_in is not None:
+            _chk_dev(state_in, "state_in", torch.float64, self.n)
         p = self.params()
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
@@ -205,17 +215,23 @@ class EnvBatch:
         self.state = out_obs  # the newest observations ARE the state (no copy)
         return out_obs, out_reward, out_done
 
-    def step_trusted(self, action, out_obs, out_reward, out_done, out_terminal=None):
+    def step_trusted(self, action, out_obs, out_reward, out_done, out_terminal=None, extra=None):
         """step() for a caller that owns correctly shaped, typed, contiguous CUDA buffers (FishingVecEnv's alternating
         output sets; `action` already coerced): no argument validation, no default allocations -- about 4 us less Python
-        per call."""
+        per call.  extra: a prepared _native.FishingStepExtra (episode statistics / float32 copies, fishing_step_ex)."""
         src = self.state
         p = self.params()
         if self.torch.cuda.current_device() != self.device.index:
             self.torch.cuda.set_device(self.device)
-        rc = self._lib.fishing_step(ct.byref(p), self.n, self.env_id0, self.step_idx, action.data_ptr(), _act_dtype(action),
-                                    None, None, self.soa(src), out_obs.data_ptr(), out_reward.data_ptr(), out_done.data_ptr(),
-                                    _ptr(out_terminal), None, None, self._raw_stream(self.device.index))
+        if extra is None:
+            rc = self._lib.fishing_step(ct.byref(p), self.n, self.env_id0, self.step_idx, action.data_ptr(), _act_dtype(action),
+                                        None, None, self.soa(src), out_obs.data_ptr(), out_reward.data_ptr(), out_done.data_ptr(),
+                                        _ptr(out_terminal), None, None, self._raw_stream(self.device.index))
+        else:
+            rc = self._lib.fishing_step_ex(ct.byref(p), self.n, self.env_id0, self.step_idx, action.data_ptr(), _act_dtype(action),
+                                           None, None, self.soa(src), out_obs.data_ptr(), out_reward.data_ptr(),
+                                           out_done.data_ptr(), _ptr(out_terminal), ct.byref(extra),
+                                           self._raw_stream(self.device.index))
         if rc:
             nat.check(rc, "fishing_step")
         self._drift(1)

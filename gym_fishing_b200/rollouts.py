@@ -43,7 +43,9 @@ def rollout_stats(env_id, num_envs, T, *, policy="escapement", S=None, msy_q=Non
                  **growth_kwargs(kind, env_kwargs))
     b.reset()
     out = b.rollout(T, policy=policy, S=S, msy_q=msy_q, freeze_done=freeze_done)
-    groups = 256 if (hi - lo) % 256 == 0 else 1          # fixed 256-wide tree: partition-invariant, see DESIGN.md section 7
+    # fixed 256-wide tree (partition-invariant) when EVERY rank's shard is a multiple of 256 --
+    # decided from the global size, so that all ranks agree on the shape of the block they exchange
+    groups = 256 if num_envs % (256 * world) == 0 else 1
     local = b.reduce_stats(out["ret"], out["done_step"], groups=groups)
     total = allreduce_stats(local, deterministic=deterministic)
     from .distributed import tree_sum

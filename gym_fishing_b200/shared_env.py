@@ -124,8 +124,10 @@ def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=Non
 
     kind = nat.KIND_OF_ID[env_id]
     cfg = normalise_kwargs(kind, env_kwargs)
-    if kind in nat.LOGNORMAL_KINDS and (S is None and msy_q is None):
-        raise ValueError("pass S / msy_q for fishing-v5..v11 (use models.policies.BMSY(env) on a scalar env)")
+    if kind in nat.LOGNORMAL_KINDS and (S is None or (policy == "msy" and msy_q is None)):
+        # the device BMSY kernel only knows the logistic / tipping-point models: never let it stand in for this family
+        raise ValueError("fishing-v5..v11: pass S (and msy_q for policy='msy'); models.policies.BMSY / msy on a scalar env "
+                         "compute them for the log-normal growth family")
     if S is None or (policy == "msy" and msy_q is None):
         S0, q0 = bmsy(kind, r=cfg["r"], K=cfg["K"], C=cfg["C"], K_is_f64=(kind == nat.V4))
         S = S0 if S is None else S

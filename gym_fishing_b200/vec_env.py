@@ -24,6 +24,13 @@ from . import _native as nat
 from .engine import EnvBatch
 from .spaces import Discrete, unit_box
 
+try:  # a real stable-baselines3 (absent from the build image): be one of ITS VecEnvs, so that PPO("MlpPolicy", venv) takes
+    # the object as it is instead of wrapping it in DummyVecEnv (tests/test-PPO.py:9-21 of the reference, pinned
+    # stable-baselines3==0.9.0 in examples/requirements.txt:29)
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase  # type: ignore
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+
 _CTOR_KEYS = {
     nat.V0: ("r", "K", "sigma", "n_actions", "init_state", "Tmax"),
     nat.V1: ("r", "K", "sigma", "init_state", "Tmax"),
@@ -138,6 +145,40 @@ class LazyInfos:
     def __iter__(self):
         return (self[i] for i in range(len(self)))
 
+    # vectorised views: nobody has to walk 2^20 dictionaries to find the handful of episodes that ended
+    def done_indices(self):
+        """indices of the environments whose episode ended in this step (numpy int64 array)."""
+        d = self._done
+        if hasattr(d, "nonzero") and not isinstance(d, np.ndarray):      # torch tensor
+            return d.nonzero().reshape(-1).cpu().numpy()
+        return np.flatnonzero(np.asarray(d))
+
+    def episode_arrays(self):
+        """(indices, returns, lengths) of the episodes that ended in this step -- the content of every infos[i]["episode"]
+        at once.  Needs monitor=True."""
+        if self._episode is None:
+            raise ValueError("episode statistics are kept with FishingVecEnv(..., monitor=True)")
+        idx = self.done_indices()
+        r, l = self._episode
+        if hasattr(r, "cpu"):
+            import torch
+
+            j = torch.as_tensor(idx, device=r.device)
+            return idx, r[j].cpu().numpy(), l[j].cpu().numpy()
+        return idx, np.asarray(r)[idx], np.asarray(l)[idx]
+
+    def terminal_observations(self):
+        """(indices, terminal observations [k, 1]) of the episodes that ended in this step."""
+        idx = self.done_indices()
+        if self._terminal is None:
+            return idx, np.empty((0, 1))
+        t = self._terminal
+        if hasattr(t, "cpu"):
+            import torch
+
+            return idx, t[torch.as_tensor(idx, device=t.device)].cpu().numpy().reshape(-1, 1)
+        return idx, np.asarray([t[i] for i in idx], dtype=np.float64).reshape(-1, 1)
+
 
 class _LazyTerminal:
     """Terminal observations of the latest numpy-mode step, copied from the device the first time one is read."""
@@ -174,14 +215,21 @@ class _PinnedArray:
             self.ptr = None
 
 
-class FishingVecEnv:
+class FishingVecEnv(_VecEnvBase):
+    """A subclass of stable_baselines3.common.vec_env.VecEnv when that package is importable (a plain class otherwise): the
+    whole abstract surface -- reset, step_async, step_wait, close, get_attr, set_attr, env_method, env_is_wrapped, seed -- is
+    implemented here, so an SB3 algorithm takes the object as its vectorised environment unchanged."""
+
     def __init__(self, env_id="fishing-v1", num_envs=1, *, device="cuda", io="torch", seed=0, auto_reset=True,
-                 env_id_offset=0, monitor=False, sb3_dtypes=False, **env_kwargs):
-        """monitor=True (torch mode): keep per-env episode return / length on the device and report them in
-        infos[i]["episode"] = {"r", "l"} when an episode ends, like stable-baselines3's VecMonitor.
+                 env_id_offset=0, monitor=False, sb3_dtypes=False, packed_done=False, **env_kwargs):
+        """monitor=True (torch mode): keep per-env episode return / length on the device -- inside the step kernel -- and
+        report them in infos[i]["episode"] = {"r", "l"} when an episode ends, like stable-baselines3's VecMonitor
+        (infos.episode_arrays() returns all of them at once).
         sb3_dtypes=True: observations and rewards come back as float32, which is what a stable-baselines3 VecEnv hands
         to the learner (the observation space is declared float32 and DummyVecEnv stores rewards in a float32 buffer);
-        the state itself stays float64 on the device.  In numpy mode this halves the PCIe traffic."""
+        the state itself stays float64 on the device, the step kernel writes the float32 copies.  In numpy mode this
+        halves the PCIe traffic.
+        packed_done=True (numpy mode, step_many): the done flags cross PCIe bit-packed and are unpacked on the host."""
         if env_id not in nat.KIND_OF_ID:
             raise KeyError(f"unknown environment id {env_id!r}")
         if io not in ("torch", "numpy"):
@@ -202,9 +250,17 @@ class FishingVecEnv:
         self.metadata = {"render.modes": ["human"]}
         self._pending = None
         self.sb3_dtypes = bool(sb3_dtypes)
+        self.packed_done = bool(packed_done)
         self.monitor = bool(monitor)
         if self.monitor and io != "torch":
             raise ValueError("monitor=True needs io='torch'")
+        if self.packed_done and (io != "numpy" or self.num_envs % 2):
+            raise ValueError("packed_done=True needs io='numpy' and an even number of environments")
+        if _VecEnvBase is not object:   # let stable-baselines3 set up its own bookkeeping (render_mode, reset_infos, ...)
+            try:
+                _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
+            except TypeError:
+                pass
         self._steps_done = 0
         self._closed = False
         self._handle = None
@@ -224,11 +280,26 @@ class FishingVecEnv:
             self._flip = 0
             self._act_dtype = torch.int64 if self.kind == nat.V0 else torch.float64
             self.terminal_obs = torch.full((self.num_envs,), float("nan"), dtype=torch.float64, device=self.device)
+            # what the step kernel keeps besides the reference's outputs (fishing_step_ex): episode statistics and float32
+            # copies of observations / rewards -- one prepared argument block per output set
+            self._extra = None
             if self.monitor:
                 self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
-                self.ep_length = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
                 self.last_ep_return = torch.zeros_like(self.ep_return)
-                self.last_ep_length = torch.zeros_like(self.ep_length)
+                self.last_ep_length = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            if self.sb3_dtypes:
+                self._obs32 = [torch.empty(self.num_envs, dtype=torch.float32, device=self.device) for _ in range(2)]
+                self._reward32 = [torch.empty(self.num_envs, dtype=torch.float32, device=self.device) for _ in range(2)]
+            if self.monitor or self.sb3_dtypes:
+                self._extra = []
+                for k in range(2):
+                    x = nat.FishingStepExtra()
+                    if self.monitor:
+                        x.ep_return, x.last_ep_return = self.ep_return.data_ptr(), self.last_ep_return.data_ptr()
+                        x.last_ep_length = self.last_ep_length.data_ptr()
+                    if self.sb3_dtypes:
+                        x.out_obs32, x.out_reward32 = self._obs32[k].data_ptr(), self._reward32[k].data_ptr()
+                    self._extra.append(x)
         else:
             import torch
 
@@ -268,7 +339,6 @@ class FishingVecEnv:
             s = self.batch.reset()
             if self.monitor:
                 self.ep_return.zero_()
-                self.ep_length.zero_()
             return s.view(self.num_envs, 1).float() if self.sb3_dtypes else s.view(self.num_envs, 1)
         nat.check(nat.lib().fishing_vec_reset(self._handle, self._h_obs.array.ctypes.data), "fishing_vec_reset")
         obs = self._h_obs.array.reshape(self.num_envs, 1)
@@ -317,20 +387,14 @@ class FishingVecEnv:
         self._flip ^= 1
         k = self._flip
         obs, rew, done = b.step_trusted(a, self._obs2[k], self._reward2[k], self._done2[k],
-                                        self.terminal_obs if self.auto_reset else None)
+                                        self.terminal_obs if self.auto_reset else None,
+                                        self._extra[k] if self._extra is not None else None)
         done_b = done.view(b.torch.bool)
-        episode = None
-        if self.monitor:
-            self.ep_return += rew
-            self.ep_length += 1
-            b.torch.where(done_b, self.ep_return, self.last_ep_return, out=self.last_ep_return)
-            b.torch.where(done_b, self.ep_length, self.last_ep_length, out=self.last_ep_length)
-            self.ep_return.masked_fill_(done_b, 0.0)
-            self.ep_length.masked_fill_(done_b, 0)
-            episode = (self.last_ep_return, self.last_ep_length)
+        episode = (self.last_ep_return, self.last_ep_length) if self.monitor else None
+        infos = LazyInfos(done, self.terminal_obs, episode)
         if self.sb3_dtypes:
-            return obs.view(self.num_envs, 1).float(), rew.float(), done_b, LazyInfos(done, self.terminal_obs, episode)
-        return obs.view(self.num_envs, 1), rew, done_b, LazyInfos(done, self.terminal_obs, episode)
+            return self._obs32[k].view(self.num_envs, 1), self._reward32[k], done_b, infos
+        return obs.view(self.num_envs, 1), rew, done_b, infos
 
     def step_into(self, actions, out_obs, out_reward, out_done, out_terminal=None, noise=None):
         """torch mode, rollout-buffer form: write this step's observations / rewards / dones straight into the given
@@ -407,16 +471,30 @@ class FishingVecEnv:
             a = a if a.dtype == np.float32 else a.astype(np.float64, copy=False)
         a = np.ascontiguousarray(a.reshape(T, n))
         fdt = np.float32 if self.sb3_dtypes else np.float64
+        done_shape = (T, (n + 7) // 8) if self.packed_done else (T, n)
         if out is None:
-            out = (np.empty((T, n), dtype=fdt), np.empty((T, n), dtype=fdt), np.empty((T, n), dtype=np.uint8))
+            out = (np.empty((T, n), dtype=fdt), np.empty((T, n), dtype=fdt), np.empty(done_shape, dtype=np.uint8))
         obs, rew, done = out
         if obs.dtype != fdt or rew.dtype != fdt:
             raise TypeError(f"output arrays must be {np.dtype(fdt).name}")
-        fn = nat.lib().fishing_vec_step_many_f32 if self.sb3_dtypes else nat.lib().fishing_vec_step_many
-        rc = fn(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data, done.ctypes.data)
+        if done.shape != done_shape or done.dtype != np.uint8:
+            raise ValueError(f"the done array must be uint8 {done_shape}" + (" (bit-packed)" if self.packed_done else ""))
+        wire = ((nat.WIRE_OBS_F32 | nat.WIRE_REWARD_F32) if self.sb3_dtypes else 0) | (nat.WIRE_DONE_BITS if self.packed_done else 0)
+        if wire:
+            rc = nat.lib().fishing_vec_step_many_wire(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data,
+                                                      done.ctypes.data, wire)
+        else:
+            rc = nat.lib().fishing_vec_step_many(self._handle, T, a.ctypes.data, adt, obs.ctypes.data, rew.ctypes.data,
+                                                 done.ctypes.data)
         nat.check(rc, "fishing_vec_step_many")
         self._steps_done += T
+        if self.packed_done:      # [T, ceil(n/8)] bytes; FishingVecEnv.unpack_dones(done) gives the [T, n] bools
+            return obs, rew, done
         return obs, rew, done.view(np.bool_)
+
+    def unpack_dones(self, packed):
+        """bit-packed done rows (packed_done=True) -> bool array [..., num_envs]."""
+        return np.unpackbits(np.asarray(packed, dtype=np.uint8), axis=-1, count=self.num_envs, bitorder="little").view(np.bool_)
 
     # ------------------------------------------------------------------------------------------------ attributes
     def _indices(self, indices):
@@ -425,6 +503,33 @@ class FishingVecEnv:
         if isinstance(indices, int):
             return [indices]
         return list(indices)
+
+    _ARRAYS = {"state": (nat.ARRAY_STATE, np.float64), "years_passed": (nat.ARRAY_YEARS, np.int32),
+               "K": (nat.ARRAY_K, np.float64), "r": (nat.ARRAY_R, np.float64), "model": (nat.ARRAY_MODEL, np.int32)}
+
+    def _per_env_array(self, attr_name):
+        """host copy of one per-environment array (numpy), whichever the io mode."""
+        if self.io == "torch":
+            b = self.batch
+            t = {"state": b.state, "years_passed": b.years, "K": b.K_env, "r": b.r_env, "model": b.model}[attr_name]
+            return None if t is None else t.cpu().numpy()
+        which, dt = self._ARRAYS[attr_name]
+        out = np.empty(self.num_envs, dtype=dt)
+        rc = nat.lib().fishing_vec_fetch_array(self._handle, which, out.ctypes.data)
+        if rc == -2:            # FISHING_E_KIND: this environment id has no such array
+            return None
+        nat.check(rc, "fishing_vec_fetch_array")
+        return out
+
+    def _store_per_env_array(self, attr_name, arr):
+        if self.io == "torch":
+            b = self.batch
+            t = {"state": b.state, "years_passed": b.years, "K": b.K_env, "r": b.r_env, "model": b.model}[attr_name]
+            t.copy_(b.torch.as_tensor(arr, device=self.device).to(t.dtype))
+            return
+        which, dt = self._ARRAYS[attr_name]
+        arr = np.ascontiguousarray(arr, dtype=dt)
+        nat.check(nat.lib().fishing_vec_store_array(self._handle, which, arr.ctypes.data), "fishing_vec_store_array")
 
     def get_attr(self, attr_name, indices=None):
         """list of per-env values (shared_env.py:73 calls env.get_attr("Tmax")[0])."""
@@ -435,28 +540,47 @@ class FishingVecEnv:
         if attr_name in shared:
             return [shared[attr_name] for _ in idx]
         if attr_name in ("K", "r"):
-            if self.kind == nat.V4 and self.io == "torch":
-                t = (self.batch.K_env if attr_name == "K" else self.batch.r_env).cpu().numpy()
-                return [float(t[i]) for i in idx]
-            if self.kind == nat.V4:
-                raise NotImplementedError("per-env K/r are device resident; use io='torch' to read them")
-            return [c[attr_name] for _ in idx]
-        if attr_name in ("state", "years_passed") and self.io == "torch":
-            t = (self.batch.state if attr_name == "state" else self.batch.years).cpu().numpy()
+            if self.kind != nat.V4:
+                return [c[attr_name] for _ in idx]
+            t = self._per_env_array(attr_name)       # fishing-v4: the parameters every environment drew at its last reset
+            return [float(t[i]) for i in idx]
+        if attr_name in ("state", "years_passed", "model"):
+            t = self._per_env_array(attr_name)
+            if t is None:
+                raise AttributeError(attr_name)
             return [np.array([t[i]]) if attr_name == "state" else int(t[i]) for i in idx]
+        if attr_name == "fish_population":
+            s, K = self._per_env_array("state"), self.get_attr("K", idx)
+            return [float((s[i] + 1) * K[j]) for j, i in enumerate(idx)]
         raise AttributeError(attr_name)
 
     def set_attr(self, attr_name, value, indices=None):
-        if indices is not None:
-            raise NotImplementedError("parameters are shared by the whole batch (except fishing-v4's drawn K, r)")
+        """Constructor parameters (r, K, sigma, C, Tmax, init_state, ...) are ONE value for the whole batch: they can be set
+        for all environments (indices=None or every index); per-environment arrays (state, years_passed, fishing-v4's K and
+        r, fishing-v11's model) can be set for any subset."""
         key = {"init_state": "x0", "K_mean": "K", "r_mean": "r"}.get(attr_name, attr_name)
+        per_env = attr_name in ("state", "years_passed", "model") or (attr_name in ("K", "r") and self.kind == nat.V4)
+        if per_env:
+            idx = list(self._indices(indices))
+            arr = self._per_env_array(attr_name)
+            if arr is None:
+                raise AttributeError(attr_name)
+            vals = np.broadcast_to(np.asarray(value, dtype=arr.dtype).reshape(-1) if np.ndim(value) else np.asarray(value, dtype=arr.dtype),
+                                   (len(idx),))
+            arr[idx] = vals
+            self._store_per_env_array(attr_name, arr)
+            return
+        if indices is not None and sorted(set(self._indices(indices))) != list(range(self.num_envs)):
+            raise ValueError(f"{attr_name!r} is one value for the whole batch (the kernels read it as a launch parameter); "
+                             "set it with indices=None, or use separate FishingVecEnv objects for separate parameter sets")
         if key not in self.cfg:
             raise AttributeError(attr_name)
         self.cfg[key] = value
         if self.io == "torch":
             self.batch.cfg["C_" if key == "C" else key] = value
         else:
-            raise NotImplementedError("set_attr after construction needs io='torch'")
+            p = self._params()
+            nat.check(nat.lib().fishing_vec_set_params(self._handle, ct.byref(p)), "fishing_vec_set_params")
 
     def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
         """Only the pure unit conversions make sense on a batch (shared_env.py:17-19 calls get_fish_population)."""
@@ -495,7 +619,13 @@ class FishingVecEnv:
         return [self._seed + i for i in range(min(self.num_envs, 8))]
 
     def render(self, mode="human"):
-        raise NotImplementedError("render() logs one CSV row per step of ONE environment; use make(id) for that")
+        """The reference's render() appends one row [years_passed, state, ...] per step of its single environment
+        (base_fishing_env.py:93-98).  For the batch: the table of all environments, columns years_passed, state (the
+        normalised observation) and fish_population -- one device-to-host copy of two arrays, nothing is drawn."""
+        s = self._per_env_array("state")
+        y = self._per_env_array("years_passed")
+        K = np.asarray(self.get_attr("K"), dtype=np.float64)
+        return np.column_stack([y.astype(np.float64), s, (s + 1) * K])
 
     def _check_open(self):
         if self._closed:

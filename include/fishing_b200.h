@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FISHING_ABI_VERSION 2
+#define FISHING_ABI_VERSION 3
 
 /* environment ids, gym_fishing/envs/__init__.py:17-35 */
 enum fishing_kind {
@@ -182,6 +182,30 @@ int fishing_step(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t s
                  double* out_harvest, void* stream);
 
 /*
+ * step with the outputs a stable-baselines3 loop wants next to the reference's (ABI v3).  Same kernel family; everything in
+ * `x` is optional (NULL):
+ *   ep_return / last_ep_return / last_ep_length  [n] each, all three or none: VecMonitor-style episode statistics kept on
+ *       the device -- ep_return accumulates the reward of the running episode; in the step that ends an episode its value
+ *       and the episode length go to last_ep_* and the accumulator restarts at 0 (stable_baselines3.common.vec_env
+ *       VecMonitor, which wraps the VecEnv the reference's tests train on: tests/test-PPO.py:9-21)
+ *   out_done_bits  the done flags bit-packed (1/8 of the bytes over PCIe)
+ *   out_obs32 / out_reward32  [n] float32 copies of out_obs / out_reward (the observation space is declared float32,
+ *       base_fishing_env.py:49-58, and DummyVecEnv keeps rewards in a float32 buffer)
+ */
+typedef struct fishing_step_extra {
+  double* ep_return;
+  double* last_ep_return;
+  int32_t* last_ep_length;
+  float* out_obs32;
+  float* out_reward32;
+  uint64_t* out_done_bits; /* [ceil(n/64)] or NULL: out_done bit-packed, bit (i & 63) of word (i >> 6) = environment i; needs the
+                              vector path (even n, even env_id0, 16-byte aligned arrays), FISHING_E_ALIGN otherwise */
+} fishing_step_extra;
+int fishing_step_ex(const fishing_params* p, int64_t n, int64_t env_id0, uint64_t step_idx, const void* action,
+                    int32_t action_dtype, const double* noise, const double* reset_noise, fishing_soa soa, double* out_obs,
+                    double* out_reward, uint8_t* out_done, double* out_terminal, const fishing_step_extra* x, void* stream);
+
+/*
  * step_many -- T consecutive lock-steps into a caller-owned rollout buffer (what an on-policy collector fills):
  * step t reads actions[t*n ..], writes out_obs / out_reward / out_done (/ out_terminal) at [t*n ..], and takes the
  * observations of step t-1 as its state, so no separate state array is read or written between steps.  One kernel
@@ -294,9 +318,27 @@ int fishing_vec_step_many(fishing_vec* v, int64_t T, const void* actions, int32_
  * state stays float64 on the device, the float32 values are its round-to-nearest casts.  Halves the PCIe traffic. */
 int fishing_vec_step_many_f32(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, float* obs_out,
                               float* reward_out, uint8_t* done_out);
+/* the general form (ABI v3): every output array picks its wire format.  obs_out / reward_out are [T, n] float64, or
+ * float32 with FISHING_WIRE_OBS_F32 / FISHING_WIRE_REWARD_F32; done_out is [T, n] uint8, or with FISHING_WIRE_DONE_BITS
+ * [T, ceil(n/8)] bytes, bit (i & 7) of byte (i >> 3) = environment i (numpy.unpackbits(..., bitorder="little")).
+ * float32 actions in, float32 observations and rewards and packed dones out is 4 + 8.125 bytes per environment-step over
+ * PCIe instead of 8 + 17. */
+enum fishing_wire { FISHING_WIRE_OBS_F32 = 1, FISHING_WIRE_REWARD_F32 = 2, FISHING_WIRE_DONE_BITS = 4 };
+int fishing_vec_step_many_wire(fishing_vec* v, int64_t T, const void* actions, int32_t action_dtype, void* obs_out,
+                               void* reward_out, void* done_out, uint32_t wire);
 /* terminal observations of the most recent step (valid where that step reported done), fetched on demand so that the
  * per-step device-to-host traffic stays at obs + reward + done */
 int fishing_vec_fetch_terminal(fishing_vec* v, double* terminal_out);
+/* Per-environment arrays of the handle, copied to / from host memory (ABI v3): what the reference exposes as attributes of
+ * each env object (state, years_passed: base_fishing_env.py:35-39; fishing-v4's drawn K, r: fishing_model_error.py:37-38)
+ * and a stable-baselines3 VecEnv reads / writes with get_attr / set_attr.  [n] float64 or int32 by array;
+ * FISHING_E_KIND when the environment id has no such array. */
+enum fishing_array { FISHING_ARRAY_STATE = 0, FISHING_ARRAY_YEARS = 1, FISHING_ARRAY_K = 2, FISHING_ARRAY_R = 3,
+                     FISHING_ARRAY_MODEL = 4, FISHING_ARRAY_TERMINAL = 5 };
+int fishing_vec_fetch_array(fishing_vec* v, int32_t which, void* out);
+int fishing_vec_store_array(fishing_vec* v, int32_t which, const void* in);
+/* replace the constructor parameters (r, K, sigma, Tmax, ... ; same environment id) -- VecEnv.set_attr on a shared parameter */
+int fishing_vec_set_params(fishing_vec* v, const fishing_params* p);
 /* device pointers of the handle's SoA state, for inspection */
 int fishing_vec_soa(fishing_vec* v, fishing_soa* out);
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/fishing_b200.h but not exported"
     assert sorted(nat.EXPORTS) == names
-    assert nat.lib().fishing_abi_version() == nat.ABI_VERSION == 2
+    assert nat.lib().fishing_abi_version() == nat.ABI_VERSION == 3
     assert b"bad argument" in nat.lib().fishing_error_string(-1)
 
 
@@ -230,8 +230,12 @@ def test_hot_kernels_keep_their_register_budget():
             name = line.split()[1].rstrip(":")
         elif line.startswith("REG:") and name:
             usage[name] = {k: int(v) for k, v in (kv.split(":") for kv in line.split() if ":" in kv and kv.split(":")[1].isdigit())}
-    k1 = [u for n, u in usage.items() if "step_kernel_vec2ILi0ELi0ELi0E" in n]     # <LOGISTIC, P_KONE, F64>
-    assert k1 and all(u["REG"] <= 32 and u["STACK"] == 0 for u in k1), k1
+    k1 = [u for n, u in usage.items() if "step_kernel_vec2ILi0ELi0ELi0E" in n and not n.endswith("ELb1EEEvNS_8StepArgsE")]   # <LOGISTIC, P_KONE, F64>
+    assert len(k1) == 2 and all(u["REG"] <= 32 and u["STACK"] == 0 for u in k1), k1      # lean and plain
+    # the EXTRA instantiation (episode statistics, float32 copies, packed dones) is a kernel of its own so that it cannot
+    # cost the two above a register; it may use up to 48 (5 resident blocks)
+    k1x = [u for n, u in usage.items() if "step_kernel_vec2ILi0ELi0ELi0E" in n and n.endswith("ELb1EEEvNS_8StepArgsE")]
+    assert len(k1x) == 1 and k1x[0]["REG"] <= 48 and k1x[0]["STACK"] == 0, k1x
     # round 2: the fused loop is unrolled twice and keeps its constants in registers (116 registers, 4 resident blocks per
     # SM): the kernel is bound by instruction issue, not latency, and measured 2.90e11 env-steps/s against 2.77e11 at 46
     # registers / 10 blocks; capping it at 80 or 64 registers spills and costs 13 - 20 % (profiles/ab_r02.md)

@@ -1,5 +1,7 @@
 """The two replicate-rollout workloads of BASELINE.json (configs 3 and 5) at test size, against known answers from the
 reference and the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -179,3 +181,64 @@ def test_full_size_cfg5_sweep_1024_levels():
     r4 = det["ret"].view(4, levels)
     assert torch.equal(r4[0], r4[1]) and torch.equal(r4[0], r4[3])
     assert float(r4[0].max()) > 75.0
+
+
+NCCL_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch
+import gym_fishing_b200 as gf
+from gym_fishing_b200.distributed import init_from_env
+rank, world, local = init_from_env()          # backend nccl: one process per GPU
+assert world == 2 and torch.distributed.get_backend() == "nccl"
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+S = float.fromhex("0x1.9374bcp-1")
+a = gf.rollout_stats("fishing-v2", 1 << 18, 200, policy="escapement", S=S, device=dev, sigma=0.05, Tmax=1000)
+b = gf.escapement_sweep("fishing-v1", levels=256, replicates=512, T=150, device=dev, sigma=0.1, Tmax=1000)
+plain = gf.rollout_stats("fishing-v2", 1 << 18, 200, policy="escapement", S=S, device=dev, sigma=0.05, Tmax=1000, deterministic=False)
+if rank == 0:
+    print("RESULT " + json.dumps({"sum": float(a["sum"]).hex(), "sumsq": float(a["sumsq"]).hex(), "n_done": float(a["n_done"]),
+                                  "sweep_sum": float(b["sum"].sum()).hex(), "sweep_sumsq_17": float(b["sumsq"][17]).hex(),
+                                  "sweep_mean_200": float(b["mean"][200]).hex(), "plain_sum": float(plain["sum"])}))
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()
+'''
+
+
+def test_two_ranks_over_nccl_reproduce_the_single_gpu_statistics(tmp_path):
+    """cfg 3 / cfg 5 in small: two processes, one GPU each, NCCL all-gather of the statistics (the only collective of the
+    path) -- the sums must be bit-identical to the one-GPU run, because the Philox streams are keyed by GLOBAL environment id and
+    the reduction tree is fixed.  Skipped on a one-GPU box; the 8-GPU records are profiles/configs_8gpu_*.jsonl."""
+    import json
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(NCCL_WORKER)
+    for attempt in range(3):
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), str(script), root]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if res.returncode == 0 or "AssertionError" in res.stderr:
+            break
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    two = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    S = float.fromhex("0x1.9374bcp-1")
+    a = gf.rollout_stats("fishing-v2", 1 << 18, 200, policy="escapement", S=S, sigma=0.05, Tmax=1000)
+    b = gf.escapement_sweep("fishing-v1", levels=256, replicates=512, T=150, sigma=0.1, Tmax=1000)
+    assert two["sum"] == float(a["sum"]).hex() and two["sumsq"] == float(a["sumsq"]).hex() and two["n_done"] == float(a["n_done"])
+    assert two["sweep_sum"] == float(b["sum"].sum()).hex() and two["sweep_sumsq_17"] == float(b["sumsq"][17]).hex()
+    assert two["sweep_mean_200"] == float(b["mean"][200]).hex()
+    assert abs(two["plain_sum"] - float(a["sum"])) <= 1e-9 * abs(float(a["sum"]))      # plain NCCL all-reduce: same value, free order

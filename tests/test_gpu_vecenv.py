@@ -478,3 +478,145 @@ def test_dqn_example_learns_on_the_discrete_env():
     spec.loader.exec_module(mod)
     rets = mod.main(["--envs", "4096", "--iters", "300"])
     assert len(rets) > 20 and rets[0] < 1.5 and max(rets[-5:]) > 2.5
+
+
+def test_wire_formats_packed_dones_and_float32_per_array():
+    """fishing_vec_step_many_wire (ABI v3): bit-packed dones and float32 observations / rewards are exactly the packed /
+    cast forms of the float64 / uint8 arrays, for an environment count that leaves a partial last word in every chunk."""
+    import gym_fishing_b200 as gf
+
+    n, T = 10_010, 12                       # even (pairs) but not a multiple of 8, 64 or the 1024-env chunk granularity
+    rng = np.random.default_rng(11)
+    acts = rng.uniform(-1, 0.2, size=(T, n))
+    kw = dict(num_envs=n, io="numpy", seed=9, sigma=0.1, Tmax=4)
+    ref = gf.FishingVecEnv("fishing-v1", **kw)
+    pk = gf.FishingVecEnv("fishing-v1", packed_done=True, **kw)
+    sb = gf.FishingVecEnv("fishing-v1", packed_done=True, sb3_dtypes=True, **kw)
+    for v in (ref, pk, sb):
+        v.reset()
+    obs, rew, done = ref.step_many(acts)
+    o1, r1, bits = pk.step_many(acts)
+    assert bits.dtype == np.uint8 and bits.shape == (T, (n + 7) // 8)
+    assert np.array_equal(o1, obs) and np.array_equal(r1, rew) and np.array_equal(pk.unpack_dones(bits), done)
+    o2, r2, bits2 = sb.step_many(acts)
+    assert o2.dtype == np.float32 and np.array_equal(o2, obs.astype(np.float32)) and np.array_equal(r2, rew.astype(np.float32))
+    assert np.array_equal(bits2, bits) and done.any() and not done.all()
+    # a second call continues the same trajectories (state, step counter, staging reuse)
+    obs_b, _, done_b = ref.step_many(acts[:5])
+    o1b, _, bits_b = pk.step_many(acts[:5])
+    assert np.array_equal(o1b, obs_b) and np.array_equal(pk.unpack_dones(bits_b), done_b)
+    with pytest.raises(ValueError, match="even"):
+        gf.FishingVecEnv("fishing-v1", num_envs=7, io="numpy", packed_done=True)
+    for v in (ref, pk, sb):
+        v.close()
+
+
+def test_step_many_host_path_equals_single_host_steps():
+    """The staged [T, chunk] pipeline of fishing_vec_step_many against T calls of fishing_vec_step, all kinds of env."""
+    import gym_fishing_b200 as gf
+
+    n, T = 6144 + 2, 9
+    rng = np.random.default_rng(2)
+    for env_id, kw in (("fishing-v1", dict(sigma=0.05, Tmax=3)), ("fishing-v2", dict(sigma=0.05, Tmax=3)),
+                       ("fishing-v4", dict(sigma=0.05, Tmax=3)), ("fishing-v0", dict(sigma=0.05, Tmax=3)),
+                       ("fishing-v10", dict(sigma=0.05, Tmax=3))):
+        acts = rng.integers(0, 60, size=(T, n)) if env_id == "fishing-v0" else rng.uniform(-1, -0.2, size=(T, n))
+        a = gf.FishingVecEnv(env_id, num_envs=n, io="numpy", seed=4, **kw)
+        b = gf.FishingVecEnv(env_id, num_envs=n, io="numpy", seed=4, **kw)
+        assert np.array_equal(a.reset(), b.reset())
+        obs, rew, done = a.step_many(acts)
+        for t in range(T):
+            o, r, d, _ = b.step(acts[t])
+            assert np.array_equal(o[:, 0], obs[t]) and np.array_equal(r, rew[t]) and np.array_equal(d, done[t]), (env_id, t)
+        a.close(), b.close()
+
+
+def test_attributes_of_the_numpy_mode_batch_and_render():
+    """get_attr / set_attr / render without a NotImplementedError: per-environment arrays travel through
+    fishing_vec_fetch_array / fishing_vec_store_array, shared parameters through fishing_vec_set_params."""
+    import gym_fishing_b200 as gf
+
+    n = 64
+    for io in ("numpy", "torch"):
+        v = gf.FishingVecEnv("fishing-v4", num_envs=n, io=io, seed=1, sigma=0.0, Tmax=50)
+        v.reset()
+        K, r = v.get_attr("K"), v.get_attr("r")
+        assert len(K) == n and len(set(K)) > n // 2 and all(0 <= k <= 1e6 for k in K) and len(set(r)) > n // 2
+        assert v.get_attr("K", indices=[3]) == [K[3]]
+        v.set_attr("K", 2.0, indices=[0, 1])               # per-environment array: any subset
+        assert v.get_attr("K", indices=[0, 1, 2]) == [2.0, 2.0, K[2]]
+        v.set_attr("state", -0.5, indices=5)
+        assert float(v.get_attr("state", indices=5)[0][0]) == -0.5
+        assert v.get_attr("years_passed") == [0] * n
+        tab = v.render()
+        assert tab.shape == (n, 3) and tab[5, 1] == -0.5 and tab[5, 2] == (-0.5 + 1) * v.get_attr("K")[5]
+        with pytest.raises(ValueError, match="whole batch"):
+            v.set_attr("sigma", 0.1, indices=[0])
+        v.set_attr("Tmax", 1)                              # shared parameter: takes effect at the next step
+        a = np.full((n, 1), -1.0)
+        if io == "torch":
+            import torch
+
+            a = torch.as_tensor(a, device="cuda")
+        _, _, d1, _ = v.step(a)
+        _, _, d2, _ = v.step(a)
+        d1 = d1.cpu().numpy() if hasattr(d1, "cpu") else d1
+        d2 = d2.cpu().numpy() if hasattr(d2, "cpu") else d2
+        assert not d1.any() and d2.all()                   # years_passed = 2 > Tmax = 1
+        v.close()
+    v1 = gf.FishingVecEnv("fishing-v1", num_envs=8, io="numpy", K=3.0)
+    v1.reset()
+    assert v1.get_attr("K") == [3.0] * 8 and v1.get_attr("fish_population") == [0.75] * 8
+    with pytest.raises(AttributeError):
+        v1.get_attr("model")
+    v1.close()
+
+
+def test_lognormal_kinds_are_refused_by_the_logistic_bmsy_and_population_draw():
+    """fishing_bmsy / fishing_population_draw only know the logistic and tipping-point models: FISHING_E_KIND for v5..v11
+    (they used to fall through to a logistic answer), and simulate_mdp_fused asks for S / msy_q instead of computing them."""
+    import ctypes as ct
+
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.shared_env import simulate_mdp_fused
+
+    S, q = ct.c_double(), ct.c_double()
+    for kind in nat.LOGNORMAL_KINDS:
+        assert nat.lib().fishing_bmsy(kind, 0.3, 1.0, 0.5, 0, ct.byref(S), ct.byref(q)) == -2
+        p = nat.make_params(kind, models=[("ricker", {"r": 0.3, "K": 1.0})] if kind == nat.V11 else None)
+        x = torch.ones(16, dtype=torch.float64, device="cuda")
+        assert nat.lib().fishing_population_draw(ct.byref(p), 16, x.data_ptr(), 0, 0.0, x.data_ptr(), None) == -2
+    assert nat.lib().fishing_bmsy(nat.V1, 0.3, 1.0, 0.5, 0, ct.byref(S), ct.byref(q)) == 0 and 0.49 < S.value < 0.51
+    with pytest.raises(ValueError, match="msy_q"):
+        simulate_mdp_fused("fishing-v6", policy="msy", reps=2, S=0.4)
+    with pytest.raises(ValueError, match="pass S"):
+        simulate_mdp_fused("fishing-v9", policy="escapement", reps=2)
+
+
+def test_step_ex_done_bits_need_the_vector_path():
+    import ctypes as ct
+
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200.engine import EnvBatch
+
+    b = EnvBatch(nat.V1, 7)                # odd n: scalar kernel
+    b.reset()
+    a = torch.zeros(7, dtype=torch.float64, device="cuda")
+    rew = torch.empty(7, dtype=torch.float64, device="cuda")
+    done = torch.empty(7, dtype=torch.uint8, device="cuda")
+    bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    o32 = torch.empty(7, dtype=torch.float32, device="cuda")
+    x = nat.FishingStepExtra(out_done_bits=bits.data_ptr())
+    p = b.params()
+    args = (ct.byref(p), 7, 0, 0, a.data_ptr(), nat.ACT_F64, None, None, b.soa(), b.state.data_ptr(), rew.data_ptr(), done.data_ptr(), None)
+    assert nat.lib().fishing_step_ex(*args, ct.byref(x), None) == -3              # FISHING_E_ALIGN
+    x = nat.FishingStepExtra(out_obs32=o32.data_ptr())
+    assert nat.lib().fishing_step_ex(*args, ct.byref(x), None) == 0              # float32 copies work on the scalar path too
+    torch.cuda.synchronize()
+    assert np.array_equal(o32.cpu().numpy(), b.state.cpu().numpy().astype(np.float32))
+    x = nat.FishingStepExtra(ep_return=rew.data_ptr())                            # statistics: all three arrays or none
+    assert nat.lib().fishing_step_ex(*args, ct.byref(x), None) == -1

@@ -22,6 +22,7 @@ VARIANTS = {
     "mb8": ["-DFISHING_K2_MINBLOCKS=8"],                  # ... 64 registers
     "mb10": ["-DFISHING_K2_MINBLOCKS=10"],                # ... 48 registers
     "unroll4": ["-DFISHING_K2_UNROLL=4"],
+    "libexp": ["-DFISHING_AB_LIBEXP"],                    # fishing-v2 with libdevice's exp instead of csrc/normal.cuh:exp_tab
     "k1smem": ["-DFISHING_K1_SMEM_TABLES"],               # K1 stages the Box-Muller tables in shared memory per block
 }
 

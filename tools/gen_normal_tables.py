@@ -104,6 +104,20 @@ def main():
     print(f"max |f (PS_fit - PS)|       = {mp.nstr(es, 5)}  (2^{mp.nstr(mp.log(es, 2), 5)})")
     print(f"max |f^2 (PC_fit - PC)|     = {mp.nstr(ec, 5)}  (2^{mp.nstr(mp.log(ec, 2), 5)})")
 
+    # ---- exp(x) for the tipping-point growth (fishing-v2): x = k ln2/64 + r, exp(x) = 2^(k >> 6) * 2^((k & 63)/64) * exp(r)
+    exp_rows = [rn(mp.mpf(2) ** (mp.mpf(j) / 64)) for j in range(64)]
+    RE = mp.log(2) / 128 * (1 + mp.mpf(2) ** -30)
+
+    def PE(r):       # (exp(r) - 1 - r) / r^2
+        return mp.mpf(1) / 2 if r == 0 else (mp.exp(r) - 1 - r) / r ** 2
+
+    pe = [rn(c) for c in cheb_fit(PE, -RE, RE, 3)]
+    ee = max_err(PE, pe, -RE, RE, lambda x: x * x)
+    print(f"max |r^2 (PE_fit - PE)|     = {mp.nstr(ee, 5)}  (2^{mp.nstr(mp.log(ee, 2), 5)})")
+    ln2_64 = mp.log(2) / 64
+    ln2_64_hi = rn(mp.mpf(float(ln2_64)) - mp.mpf(float(ln2_64)) % mp.mpf(2) ** -40)   # 64/ln2 * hi is exact for |k| < 2^17
+    ln2_64_lo = rn(ln2_64 - mp.mpf(ln2_64_hi))
+
     with open(OUT, "w") as fh:
         w = fh.write
         w("// GENERATED by tools/gen_normal_tables.py -- do not edit.  Tables and coefficients of the table-assisted Box-Muller\n"
@@ -119,6 +133,14 @@ def main():
         w(f"#define FISHING_LOG_TABLE_INIT {{ \\\n")
         for a, b in log_rows:
             w(f"  {{{hexf(a)}, {hexf(b)}}}, \\\n")
+        w("}\n\n// exp(x): 64 / ln 2, -ln2/64 split hi + lo (hi has 24 trailing zero bits), (exp(r) - 1 - r) / r^2 cubic\n")
+        w(f"#define FISHING_EXP_64_LN2 {hexf(rn(64 / mp.log(2)))}\n")
+        w(f"#define FISHING_EXP_NLN2_64_HI {hexf(-ln2_64_hi)}\n#define FISHING_EXP_NLN2_64_LO {hexf(-ln2_64_lo)}\n")
+        for k, v in enumerate(pe):
+            w(f"#define FISHING_PE{k} {hexf(v)}\n")
+        w("// 2^(j/64), j = 0..63\n#define FISHING_EXP_TABLE_INIT { \\\n")
+        for v in exp_rows:
+            w(f"  {hexf(v)}, \\\n")
         w("}\n\n// { cos, sin } of 2 pi (j/256 + 2^-53)\n")
         w(f"#define FISHING_TRIG_TABLE_INIT {{ \\\n")
         for a, b in trig_rows:
