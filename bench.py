@@ -217,6 +217,65 @@ def _ref_worker(args):
     return time.perf_counter() - t0
 
 
+def _ref_simulate_worker(args):
+    """cfg 1 on the reference: fishing-v0, escapement policy, env.simulate(model, reps) with Tmax = 1000 (shared_env.py:29-54);
+    returns (seconds, steps)."""
+    reps, seed = args
+    for p in (os.path.join(ROOT, "oracle", "refstub"), REF_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gym
+    import gym_fishing  # noqa: F401
+    import numpy as np
+    from gym_fishing.models.policies import escapement
+
+    np.random.seed(seed)
+    env = gym.make("fishing-v0", sigma=0.05, Tmax=1000)
+    model = escapement(env)
+    env.simulate(model, reps=1)
+    t0 = time.perf_counter()
+    df = env.simulate(model, reps=reps)
+    return time.perf_counter() - t0, len(df)
+
+
+def cfg1_leg(dev):
+    """BASELINE.json config 1 through the scalar drop-in API: make("fishing-v0"), escapement policy, 1000-step episodes.
+    (i) the caller's own loop over model.predict / env.step (one kernel launch + one synchronisation per step),
+    (ii) env.simulate(model, reps) -- all repetitions as one fused rollout with the reference's use of numpy's generator,
+    (iii) the unmodified reference's env.simulate on one core, when baseline/_ref is there."""
+    import numpy as np
+
+    import gym_fishing_b200 as gf
+
+    np.random.seed(0)
+    env = gf.make("fishing-v0", sigma=0.05, Tmax=1000, device=dev)
+    model = gf.escapement(env)
+    obs = env.reset()
+    for _ in range(50):
+        obs, _, _, _ = env.step(model.predict(obs)[0])
+    obs = env.reset()
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        a, _ = model.predict(obs)
+        obs, r, d, _ = env.step(a)
+    step_rate = 1000 / (time.perf_counter() - t0)
+    env.simulate(model, reps=2)
+    reps = 200
+    t0 = time.perf_counter()
+    df = env.simulate(model, reps=reps)
+    sim_rate = len(df) / (time.perf_counter() - t0)
+    out = {"workload": "cfg1: fishing-v0 (n_actions=100, sigma=0.05), constant-escapement policy, 1000-step episodes through make()",
+           "step_loop": {"value": step_rate, "unit": UNIT, "what": "1000 x (model.predict, env.step): one launch + one synchronisation per step"},
+           "simulate": {"value": sim_rate, "unit": UNIT, "reps": reps,
+                        "what": "env.simulate(escapement(env), reps): one fused rollout for all repetitions, noise drawn from numpy's "
+                                "global generator in the reference's order (gym_fishing_b200/shared_env.py:simulate_on_device)"}}
+    if reference_available():
+        sec, steps = _ref_simulate_worker((20, 0))
+        out["reference_simulate"] = {"value": steps / sec, "unit": UNIT, "reps": 20, "cores": 1,
+                                     "what": "the unmodified reference's env.simulate(escapement(env), reps) (baseline/_ref)"}
+    return out
+
+
 def cpu_loop_throughput(worker, steps_per_proc, procs):
     if procs == 1:
         return steps_per_proc / worker((steps_per_proc, 0))
@@ -347,6 +406,38 @@ def run_gpu(args):
     ms = barrier_max_ms(ms, dev)
     value = world * n * T * args.steps / (ms * 1e-3)
     k1_us = ms * 1e3 / (args.steps * launches_per_step)
+
+    # ---- the same kernel at the north-star's 2^21 envs per GPU and at 2^23 (state far beyond the L2: DRAM-resident)
+    def k1_point(n_envs, T_pt):
+        g2 = torch.Generator(device=dev).manual_seed(99 + rank)
+        a2 = torch.rand((T_pt, n_envs), dtype=torch.float64, device=dev, generator=g2) * 2 - 1
+        o2 = torch.empty((T_pt, n_envs), dtype=torch.float64, device=dev)
+        r2 = torch.empty((T_pt, n_envs), dtype=torch.float64, device=dev)
+        d2 = torch.empty((T_pt, n_envs), dtype=torch.uint8, device=dev)
+        bp = EnvBatch(nat.V1, n_envs, device=dev, env_id0=rank * n_envs, seed=0, auto_reset=True, **CFG)
+        bp.reset()
+        with torch.cuda.stream(stream):
+            bp.step_many(a2, o2, r2, d2)
+            stream.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(3):
+                bp.step_many(a2, o2, r2, d2)
+            p1.record(stream)
+            stream.synchronize()
+        us = barrier_max_ms(p0.elapsed_time(p1), dev) * 1e3 / (3 * T_pt)
+        gbs = K1_BYTES * n_envs / (us * 1e-6) / 1e9
+        return {"envs_per_gpu": n_envs, "avg_launch_us": us, "achieved": gbs, "unit": "GB/s", "value": world * n_envs / (us * 1e-6),
+                "launches": "issued from C (fishing_step_many), no graph"}
+
+    k1_points = []
+    if not args.no_configs:
+        peak_now, _ = measured_peak()
+        for n_pt, T_pt in ((1 << 21, 200), (1 << 23, 60)):
+            pt = k1_point(n_pt, T_pt)
+            pt["frac"] = pt["achieved"] / peak_now
+            k1_points.append(pt)
+        torch.cuda.empty_cache()
 
     # sanity: the timed work really happened (dones fire, rewards are finite and non-trivial)
     frac_done = float(done[-1].float().mean().item())
@@ -613,12 +704,14 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = K1_BYTES * n / (k1_us * 1e-6) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None      # NOT measured in this run: the ncu figure recorded under profiles/
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/k1_traffic.json: " + tj.get("source", "")
         except Exception:  # noqa: BLE001
             pass
+        cfg1 = cfg1_leg(dev) if (world == 1 and not args.no_cpu_baseline) else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             have_ref = reference_available()
@@ -636,8 +729,13 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step_kernel_vec2<LOGISTIC,P_KONE,F64>", "bytes_per_env_step": K1_BYTES,
-                         "avg_launch_us": k1_us, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "step_kernel_vec2<LOGISTIC,P_KONE,F64>", "bytes_per_env_step": K1_BYTES,
+                         "avg_launch_us": k1_us, "peak_source": peak_src,
+                         "note": "at 2^20 envs the state / years arrays (12 MB) live in the 126 MB L2, so the algorithmic-byte rate can pass "
+                                 "the measured DRAM copy rate; a compute-free replica of the same traffic (tools/k1_traffic_probe.cu, "
+                                 "profiles/k1_traffic_probe_r02.txt) needs 5.5 us per launch",
+                         "other_sizes": k1_points},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
@@ -655,6 +753,7 @@ def run_gpu(args):
                                                "api": "FishingVecEnv(io='numpy', sb3_dtypes=True, packed_done=True).step_many -> fishing_vec_step_many_wire (dones cross PCIe bit-packed; unpacking on the host is not timed)"}},
             "fused": fused,
             "configs": configs,
+            "cfg1": cfg1,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),
             "check": {"frac_done_last_step": frac_done, "mean_reward_last_step": mean_rew},

@@ -251,9 +251,18 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
       const int64_t block0 = 2 * (int64_t)(blockIdx.x * (unsigned)BS);
       for (int k = lane; k < total; k += 32) {
         const int64_t i = block0 + reinterpret_cast<volatile uint16_t*>(s_job)[k];
+#ifdef FISHING_AB_V4_NODRAW      // timing build: what do the draws cost (the scattered writes stay)
+        Normal2 d;
+        d.z0 = d.z1 = (double)k * 1e-3;
+#else
         const Normal2 d = normal_pair_keys(a.keys, (uint64_t)(a.env_id0 + i), a.step_idx, FISHING_STREAM_AUTORESET);
+#endif
+#ifndef FISHING_AB_V4_NOWRITE    // timing build: what do the scattered 8-byte writes cost (the draws stay)
         a.K_env[i] = v4_param(a.K_mean, a.sigma_p, d.z0);
         a.r_env[i] = v4_param(a.r_mean, a.sigma_p, d.z1);
+#else
+        if (d.z0 == 1.2345e300) a.K_env[i] = d.z1;
+#endif
       }
     }
   }

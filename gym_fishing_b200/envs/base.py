@@ -284,9 +284,13 @@ class BaseFishingEnv(_EnvBase):
 
     # ------------------------------------------------------------------------------------------------ reporting
     def simulate(env, model, reps=1):
-        from ..shared_env import simulate_mdp
+        """simulate_mdp (shared_env.py:29-54).  With this package's escapement / msy policy the repetitions run as one fused
+        rollout on the device (shared_env.simulate_on_device: same table, same use of numpy's generator); any other model
+        -- an SB3 agent, a user policy -- goes through the host loop over step()."""
+        from ..shared_env import simulate_mdp, simulate_on_device
 
-        return simulate_mdp(env, model, reps)
+        df = simulate_on_device(env, model, reps)
+        return df if df is not None else simulate_mdp(env, model, reps)
 
     def policyfn(env, model, reps=1):
         from ..shared_env import estimate_policyfn

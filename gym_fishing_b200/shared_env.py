@@ -7,6 +7,7 @@ import numpy as np
 from pandas import DataFrame
 
 COLUMNS = ["time", "state", "action", "reward", "rep"]
+_NUMPY_NORMAL = np.random.normal      # to notice a test harness that has replaced the global generator's draw function
 
 
 def simulate_mdp(env, model, reps=1):
@@ -108,14 +109,16 @@ def plot_policyfn(self, df, output="policy.png"):
     plt.close("all")
 
 
-def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=None, noise=None, seed=0, device="cuda",
-                       **env_kwargs):
+def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=None, noise=None, reset_noise=None, seed=0,
+                       device="cuda", return_steps=False, **env_kwargs):
     """simulate_mdp (shared_env.py:29-54) for one of the built-in policies with ALL repetitions run as one fused rollout on
     the device: `reps` environments, at most Tmax steps, an environment stops at its first done (the `break` at :51).
     Returns the same table [time, state, action, reward, rep] (same one-step lag of the quota / reward columns).
 
     policy: "escapement" (S = BMSY by default) or "msy" (msy_q = surplus production at BMSY by default);
-    noise: optional [Tmax, reps] standard normals to inject (else the engine's Philox stream keyed by `seed`)."""
+    noise: optional [Tmax, reps] standard normals to inject (else the engine's Philox stream keyed by `seed`);
+    reset_noise: optional [2, reps] (zK, zr) for the parameter draws of fishing-v4's reset;
+    return_steps: also return the number of steps every repetition took."""
     import torch
 
     from . import _native as nat
@@ -132,11 +135,17 @@ def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=Non
         S0, q0 = bmsy(kind, r=cfg["r"], K=cfg["K"], C=cfg["C"], K_is_f64=(kind == nat.V4))
         S = S0 if S is None else S
         msy_q = q0 if msy_q is None else msy_q
-    n = int(reps) + (int(reps) & 1)          # the fused kernel owns environments in pairs
+    reps = int(reps)
+    n = reps + (reps & 1)          # the fused kernel owns environments in pairs
     T = int(cfg["Tmax"])
     b = EnvBatch(kind, n, device=device, seed=seed, r=cfg["r"], K=cfg["K"], sigma=cfg["sigma"], C=cfg["C"], x0=cfg["x0"],
                  Tmax=T, n_actions=cfg["n_actions"], sigma_p=cfg["sigma_p"], **growth_kwargs(kind, env_kwargs))
-    b.reset()
+    if reset_noise is not None:
+        zr = torch.zeros((2, n), dtype=torch.float64, device=b.device)
+        zr[:, :reps] = torch.as_tensor(np.asarray(reset_noise, dtype=np.float64), device=b.device).reshape(2, reps)
+        b.reset(reset_noise=zr.contiguous())
+    else:
+        b.reset()
     obs0 = b.state.clone()
     K = b.K_env.clone() if b.K_env is not None else torch.full((n,), float(cfg["K"]), dtype=torch.float64, device=b.device)
     if noise is not None:
@@ -146,18 +155,93 @@ def simulate_mdp_fused(env_id, policy="escapement", reps=1, *, S=None, msy_q=Non
     out = b.rollout(T, policy=policy, S=float(S), msy_q=None if msy_q is None else float(msy_q), noise=noise,
                     freeze_done=True, trace=True, trace_action=True)
     obs, rew, act = out["obs"].cpu().numpy(), out["reward"].cpu().numpy(), out["action"].cpu().numpy()
-    dstep = out["done_step"].cpu().numpy()
+    dstep = out["done_step"].cpu().numpy()[:reps]
     obs0, K = obs0.cpu().numpy(), K.cpu().numpy()
-    chunks = []
-    for rep in range(int(reps)):
-        L = T if dstep[rep] < 0 else int(dstep[rep]) + 1           # steps actually taken
-        s_before = np.concatenate([[obs0[rep]], obs[:L - 1, rep]])
-        a_prev = act[:L - 1, rep]
-        if kind == nat.V0:
-            quota = (a_prev / cfg["n_actions"]) * K[rep]
-        else:
-            quota = (np.clip(a_prev, -1.0, 1.0) + 1) * K[rep]
-        chunks.append(np.column_stack([np.arange(L), (s_before + 1) * K[rep], np.concatenate([[0.0], quota]),
-                                       np.concatenate([[0.0], rew[:L - 1, rep]]), np.full(L, rep)]))
-    df = DataFrame(np.concatenate(chunks), columns=COLUMNS)
-    return df.astype({"time": int, "rep": int})
+    steps = np.where(dstep < 0, T, dstep + 1).astype(np.int64)          # steps actually taken by every repetition
+    # the table, built for all repetitions at once: row (t, rep) exists for t < steps[rep]
+    tt, rr = np.meshgrid(np.arange(T), np.arange(reps), indexing="ij")
+    keep = tt < steps[None, :]
+    s_before = np.concatenate([obs0[None, :reps], obs[:T - 1, :reps]], axis=0)
+    a_prev = np.concatenate([np.zeros((1, reps)), act[:T - 1, :reps]], axis=0)
+    Kr = K[None, :reps]
+    quota = (a_prev / cfg["n_actions"]) * Kr if kind == nat.V0 else (np.clip(a_prev, -1.0, 1.0) + 1) * Kr
+    quota[0, :] = 0.0
+    r_prev = np.concatenate([np.zeros((1, reps)), rew[:T - 1, :reps]], axis=0)
+    order = np.argsort(rr[keep], kind="stable")                           # rows grouped by repetition, time ascending
+    table = np.column_stack([tt[keep], ((s_before + 1) * Kr)[keep], quota[keep], r_prev[keep], rr[keep]])[order]
+    df = DataFrame(table, columns=COLUMNS).astype({"time": int, "rep": int})
+    return (df, steps) if return_steps else df
+
+
+_ENV_ID_OF_KIND = {0: "fishing-v0", 1: "fishing-v1", 2: "fishing-v2", 4: "fishing-v4"}
+
+
+def simulate_on_device(env, model, reps=1):
+    """env.simulate(model, reps) without the host loop, when `model` is this package's escapement / msy policy of this very
+    environment (fishing-v0/v1/v2/v4): all repetitions run as ONE fused rollout (simulate_mdp_fused) and the table comes
+    out identical to simulate_mdp's.  Returns None when the combination is not covered -- the caller runs the host loop.
+
+    noise="philox": the engine's counter-based stream, repetition k = environment k of a fresh key.
+    noise="numpy" (the default, reference-compatible mode): the normals are drawn from numpy's GLOBAL generator in exactly
+    the order and number the reference's loop would consume them -- per repetition (2 for fishing-v4's reset,
+    fishing_model_error.py:42-43, then) one per step, a repetition that ends early leaves its unused draws to the next one
+    (shared_env.py:51) -- and injected into the kernel, so np.random.seed(s) gives the reference's table bit for bit and
+    leaves the generator where the reference leaves it.  Because the number of steps is only known afterwards, the run is
+    repeated with corrected offsets when a repetition ended early: every pass fixes at least the first repetition whose
+    offset was wrong, so a handful of early endings converge in a few passes; after six the host loop takes over (a
+    policy that drives most repetitions extinct is inherently sequential in the reference's draw order)."""
+    from . import _native as nat
+    from .models.policies import escapement, msy
+
+    kind = env._kind
+    if kind not in _ENV_ID_OF_KIND or type(model) not in (escapement, msy) or getattr(model, "env", None) is not env:
+        return None
+    if int(reps) < 1 or int(env.Tmax) < 1:
+        return None
+    policy = "msy" if type(model) is msy else "escapement"
+    kw = dict(sigma=env.sigma, init_state=env.init_state, Tmax=env.Tmax)
+    if kind == nat.V4:
+        kw.update(K_mean=env.K_mean, r_mean=env.r_mean, sigma_p=env.sigma_p)
+    else:
+        kw.update(r=env.r, K=env.K)
+    if kind == nat.V0:
+        kw["n_actions"] = env.n_actions
+    if kind == nat.V2:
+        kw["C"] = env.C
+    common = dict(policy=policy, reps=reps, S=float(model.S), msy_q=float(model.msy) if policy == "msy" else None,
+                  device=env._slot.device, **kw)
+    reps, T = int(reps), int(env.Tmax)
+    if env._noise_mode == "philox":
+        env._epoch += 1
+        df = simulate_mdp_fused(_ENV_ID_OF_KIND[kind], seed=env._seed + (env._epoch << 20), **common)
+        env.reset()
+        return df
+    if np.random.normal is not _NUMPY_NORMAL:
+        return None        # someone injects the draws call by call (the parity tests do): keep making scalar calls in order
+    per_reset = 2 if kind == nat.V4 else 0
+    state0 = np.random.get_state()
+    steps = np.full(reps, T, dtype=np.int64)
+    for _ in range(6):
+        np.random.set_state(state0)
+        per_rep = steps + per_reset
+        z = np.random.normal(0, 1, size=int(per_rep.sum()))            # the legacy generator: same stream as scalar calls
+        offs = np.concatenate([[0], np.cumsum(per_rep)[:-1]])
+        noise = np.zeros((T, reps))
+        tt = np.arange(T)[:, None]
+        valid = tt < steps[None, :]
+        noise[valid] = z[(offs[None, :] + per_reset + tt)[valid]]
+        reset_noise = np.stack([z[offs], z[offs + 1]]) if per_reset else None
+        df, took = simulate_mdp_fused(_ENV_ID_OF_KIND[kind], noise=noise, reset_noise=reset_noise, return_steps=True, **common)
+        if np.array_equal(took, steps):
+            _leave_like_the_host_loop(env)
+            return df
+        steps = took
+    np.random.set_state(state0)
+    return None
+
+
+def _leave_like_the_host_loop(env):
+    """After the device run: counters as after a reset (the generator has already been advanced by the draws that were used)."""
+    env.years_passed = 0
+    env.reward = 0
+    env.harvest = 0

@@ -620,3 +620,52 @@ def test_step_ex_done_bits_need_the_vector_path():
     assert np.array_equal(o32.cpu().numpy(), b.state.cpu().numpy().astype(np.float32))
     x = nat.FishingStepExtra(ep_return=rew.data_ptr())                            # statistics: all three arrays or none
     assert nat.lib().fishing_step_ex(*args, ct.byref(x), None) == -1
+
+
+def test_env_simulate_runs_on_the_device_with_the_reference_use_of_numpys_generator():
+    """env.simulate(escapement | msy) as ONE fused rollout (shared_env.simulate_on_device): the table and the state of
+    numpy's global generator afterwards are those of the host loop over step() -- i.e. of the reference's simulate_mdp
+    (shared_env.py:29-54) -- including repetitions that end early and fishing-v4's two draws per reset."""
+    import gym_fishing_b200 as gf
+    from gym_fishing_b200.shared_env import simulate_mdp, simulate_on_device
+
+    cases = [("fishing-v1", dict(sigma=0.05, Tmax=40), "escapement", 7), ("fishing-v0", dict(sigma=0.1, Tmax=25), "msy", 6),
+             ("fishing-v2", dict(sigma=0.08, Tmax=30), "escapement", 5), ("fishing-v4", dict(sigma=0.05, Tmax=20), "escapement", 6),
+             # constant quotas under strong noise: some repetitions go extinct and end early (the draws they leave unused
+             # move to the next repetition); with many of them the device route gives up and the host loop answers
+             ("fishing-v1", dict(sigma=0.25, Tmax=60), "msy", 12), ("fishing-v1", dict(sigma=0.4, Tmax=60), "msy", 12),
+             ("fishing-v1", dict(sigma=0.9, Tmax=60), "msy", 12)]
+    early_on_device = 0
+    for env_id, kw, pol, reps in cases:
+        np.random.seed(123)
+        env = gf.make(env_id, **kw)
+        model = {"escapement": gf.escapement, "msy": gf.msy}[pol](env)
+        st = np.random.get_state()
+        host = simulate_mdp(env, model, reps)
+        after_host = np.random.get_state()[1].copy(), np.random.get_state()[2:]
+        n_early = reps - int((host.groupby("rep").size() == kw["Tmax"]).sum())
+        np.random.set_state(st)
+        dev = simulate_on_device(env, model, reps)
+        assert dev is not None or n_early > 2, (env_id, kw, n_early)
+        np.random.set_state(st)
+        pub = env.simulate(model, reps)                               # the public entry point: device route, else the host loop
+        after_pub = np.random.get_state()[1].copy(), np.random.get_state()[2:]
+        assert np.array_equal(after_host[0], after_pub[0]) and after_host[1] == after_pub[1], (env_id, kw)   # same draws consumed
+        assert list(pub.columns) == list(host.columns) and len(pub) == len(host), (env_id, len(pub), len(host))
+        tol = 1e-12 if env_id == "fishing-v2" else 0.0
+        a, b = pub.values.astype(np.float64), host.values.astype(np.float64)
+        assert np.all(np.abs(a - b) <= tol * np.maximum(np.abs(b), 1.0)), (env_id, kw)
+        if dev is not None:
+            assert dev.equals(pub)
+            early_on_device += int(n_early > 0)
+    assert early_on_device >= 1, "no case with an early ending went through the device route"
+    # Philox mode: no host generator involved, repetitions are independent environments
+    env = gf.make("fishing-v1", sigma=0.1, Tmax=50, noise="philox", seed=3)
+    df = env.simulate(gf.escapement(env), reps=200)
+    assert len(df) == 200 * 50 and df.groupby("rep").reward.sum().std() > 0
+    # a foreign model goes through the host loop
+    class Const:
+        def predict(self, obs, **kw):
+            return np.array([-0.9]), None
+    host_df = env.simulate(Const(), reps=2)
+    assert 2 <= len(host_df) <= 100 and set(host_df.rep) == {0, 1} and (host_df.action.iloc[1:5] > 0).all()

@@ -22,7 +22,9 @@ VARIANTS = {
     "mb8": ["-DFISHING_K2_MINBLOCKS=8"],                  # ... 64 registers
     "mb10": ["-DFISHING_K2_MINBLOCKS=10"],                # ... 48 registers
     "unroll4": ["-DFISHING_K2_UNROLL=4"],
-    "libexp": ["-DFISHING_AB_LIBEXP"],                    # fishing-v2 with libdevice's exp instead of csrc/normal.cuh:exp_tab
+    "libexp": ["-DFISHING_AB_LIBEXP"],
+    "v4nodraw": ["-DFISHING_AB_V4_NODRAW"],               # NOT the product: fishing-v4 resets without the Philox / Box-Muller work
+    "v4nowrite": ["-DFISHING_AB_V4_NOWRITE"],             # NOT the product: ... without the scattered K / r rewrites                    # fishing-v2 with libdevice's exp instead of csrc/normal.cuh:exp_tab
     "k1smem": ["-DFISHING_K1_SMEM_TABLES"],               # K1 stages the Box-Muller tables in shared memory per block
 }
 
