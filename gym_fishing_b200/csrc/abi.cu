@@ -467,12 +467,11 @@ int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int
       g = t.p[model_index];
     }
   }
-  if (p->kind == FISHING_V10) {
+  if (p->kind == FISHING_V10) {     // r <- r + alpha before the draw; the derived fields follow on the device (as in K1 / K2)
     volatile double r_next = p->r + p->alpha;
     g.r = r_next;
-    growth_derive(g, fn);
   }
-  return (int)launch_growth_ln(fn, n, x, g, z, out, static_cast<cudaStream_t>(stream));
+  return (int)launch_growth_ln(fn, n, x, g, p->kind == FISHING_V10, z, out, static_cast<cudaStream_t>(stream));
 }
 
 int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out) {

@@ -114,8 +114,8 @@ cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64
                               double* out, cudaStream_t st);
 cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r, double K, double C, double sigma,
                           double z, void* out, cudaStream_t st);
-cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
-                             cudaStream_t st);
+cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, bool derive_on_device, const double* z,
+                             double* out, cudaStream_t st);
 cudaError_t launch_fp64_probe(double* scratch, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);

@@ -584,15 +584,28 @@ cudaError_t launch_noise_fill(uint64_t seed, int32_t stream_id, int64_t n, int64
 
 // stand-alone population_draw of the log-normal family on an array, ONE draw per element like np.random.lognormal(mu)
 __global__ void __launch_bounds__(256) growth_ln_kernel(int fn, int64_t n, const double* __restrict__ x, GrowthP gp,
-                                                         const double* __restrict__ z, double* __restrict__ out) {
+                                                         int derive_on_device, const double* __restrict__ z,
+                                                         double* __restrict__ out) {
+  // fishing-v10: log(A) and B follow the drifting r; derived with the DEVICE's log, like K1 and K2 do (StepArgs::derive_on_device)
+  if (derive_on_device) growth_derive(gp, fn);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = grow_by_model(fn, x[i], gp, z ? z[i] : 0.0, true);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double zi = z ? z[i] : 0.0;
+    double v;
+    switch (fn) {    // kernel-uniform: the same device functions as the single-model K1 / K2 instantiations (bit-identical)
+      case FISHING_FN_ALLEN: v = grow_lognormal<FISHING_FN_ALLEN>(x[i], gp, zi, true); break;
+      case FISHING_FN_BEVERTON_HOLT: v = grow_lognormal<FISHING_FN_BEVERTON_HOLT>(x[i], gp, zi, true); break;
+      case FISHING_FN_MYERS: v = grow_lognormal<FISHING_FN_MYERS>(x[i], gp, zi, true); break;
+      case FISHING_FN_MAY: v = grow_lognormal<FISHING_FN_MAY>(x[i], gp, zi, true); break;
+      default: v = grow_lognormal<FISHING_FN_RICKER>(x[i], gp, zi, true); break;
+    }
+    out[i] = v;
+  }
 }
 
-cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, const double* z, double* out,
-                             cudaStream_t st) {
-  growth_ln_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(fn, n, x, gp, z, out);
+cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, bool derive_on_device, const double* z,
+                             double* out, cudaStream_t st) {
+  growth_ln_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(fn, n, x, gp, derive_on_device ? 1 : 0, z, out);
   count_launch();
   return cudaGetLastError();
 }

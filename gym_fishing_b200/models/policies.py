@@ -14,8 +14,11 @@ from ..engine import bmsy as _bmsy_kernel
 
 
 def BMSY(env):
-    """Stock size with maximum deterministic surplus production.  np.float32 for v0/v1/v2, np.float64 for v4,
-    exactly as the reference returns it.  Resets the environment."""
+    """Stock size with maximum deterministic surplus production.  fishing-v0/v1/v2/v4: the value the reference returns, bit
+    for bit (np.float32, np.float64 for v4).  fishing-v5..v11: the same procedure, but the surplus curve is evaluated in
+    float64 where the reference's float32 grid makes numpy's `log` / `power` float32; the curve is flat to ~1e-8 around its
+    maximum, so S can land on a neighbouring point of the 10001-point grid (tests/test_gpu_lognormal.py bounds it by two grid
+    steps).  Resets the environment."""
     kind = env._kind
     if kind in nat.LOGNORMAL_KINDS:
         # fishing-v5..v11: no fused kernel; same procedure as the reference through the env's own (device) population_draw
