@@ -60,7 +60,7 @@ def _run(cmd):
         return True, str(e)
 
 
-def build(force=False, verbose=False, extra_flags=(), out=None):
+def build(force=False, verbose=False, extra_flags=(), out=None, sources=SOURCES):
     """Compile every CUDA source into gym_fishing_b200/libfishing_b200.so (one nvcc per source, in parallel, then one
     link).  `extra_flags` / `out` build a variant of the same library for A/B runs (see _native.FISHING_B200_LIB).
     Returns the library path."""
@@ -73,8 +73,8 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     os.makedirs(objdir, exist_ok=True)
     flags = ([f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas=-v"] if verbose else []) +
              ['-DFISHING_BUILD_ID_STR="' + source_id(extra_flags) + '"'])
-    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
-    cmds = [[_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", o] for s, o in zip(SOURCES, objs)]
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in sources]
+    cmds = [[_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", o] for s, o in zip(sources, objs)]
     with ThreadPoolExecutor(len(cmds)) as ex:
         results = list(ex.map(_run, cmds))
     failed = any(f for f, _ in results)

@@ -107,6 +107,17 @@ static bool pdl_enabled() {
   return on;
 }
 
+// K1's phase-A prefetch of the state lines: on when one launch's state (state + years, + K and r for fishing-v4) is larger
+// than ~2/3 of the 126 MB L2, i.e. when consecutive lock-steps find it in DRAM.  FISHING_K1_PREFETCH=0 / 1 forces it.
+static bool k1_prefetch(int64_t state_bytes) {
+  static const int forced = [] {
+    const char* e = std::getenv("FISHING_K1_PREFETCH");
+    return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+  }();
+  if (forced >= 0) return forced == 1;
+  return state_bytes >= (int64_t)80 << 20;
+}
+
 // device-side address of a page-locked host allocation (NULL if the pointer is ordinary pageable memory)
 static void* device_alias(const void* host) {
   cudaPointerAttributes at;
@@ -166,6 +177,9 @@ int fishing_abi_version(void) { return FISHING_ABI_VERSION; }
 // script read it from the file without loading the library
 #ifndef FISHING_BUILD_ID_STR
 #define FISHING_BUILD_ID_STR "unknown"
+#endif
+#ifdef FISHING_BUILD_SELFTEST_FAIL   // tests/test_cpu_host.py: a compile error must make the build fail loudly
+#error "deliberate compile error (FISHING_BUILD_SELFTEST_FAIL)"
 #endif
 const char* fishing_build_id(void) {
   static const char id[] = "FISHING_BUILD_ID=" FISHING_BUILD_ID_STR;
@@ -314,6 +328,7 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   if (vec && (n >> 1) > 0x7fffffffLL) vec = false;
   if (a.out_done_bits && !vec) return FISHING_E_ALIGN;   // the bit packing is a warp ballot of the pair-per-thread kernel
   if (vec && (p->flags & FISHING_PDL) && pdl_enabled()) a.flags |= STEP_FLAG_PDL;
+  if (vec && k1_prefetch(n * (p->kind == FISHING_V4 ? 28 : 12))) a.flags |= STEP_FLAG_PREFETCH;
   return (int)launch_step(a, p->kind, action_dtype, vec, static_cast<cudaStream_t>(stream));
 }
 

@@ -198,7 +198,7 @@ template <int FN>
 __device__ __forceinline__ double grow_lognormal(double x1, const GrowthP& g, double z, bool noisy) {
   double e = lognormal_mu<FN>(x1, g);
   if (noisy) e = __dadd_rn(e, __dmul_rn(g.sigma, z));
-  const double v = exp(e);
+  const double v = exp_tab(e, GlobalTabs());     // csrc/normal.cuh: table-assisted, <= 1.02 ulp (the family's parity is a tolerance)
   return (0.0 > v) ? 0.0 : v;
 }
 
@@ -213,7 +213,7 @@ __device__ __forceinline__ double grow_lognormal(double x1, const GrowthP& g, do
 __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP& g, double z, bool noisy) {
   const double lx = log(x1);    // x1 >= +0 or NaN here, so Beverton-Holt's np.clip(x, 0, inf) is the identity
   const bool has_pow = fn == FISHING_FN_MYERS || fn == FISHING_FN_MAY;
-  const double pw = exp(__dmul_rn(fn == FISHING_FN_MYERS ? g.theta : g.q, lx));        // x^theta / x^q (unused otherwise)
+  const double pw = exp_tab(__dmul_rn(fn == FISHING_FN_MYERS ? g.theta : g.q, lx), GlobalTabs());   // x^theta / x^q (unused otherwise)
   double base = 0.0, arg = 1.0;
   switch (fn) {
     case FISHING_FN_ALLEN:           // np.log(x) + r * (1 - x / K) * (1 - C) / K
@@ -239,7 +239,7 @@ __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP
   const double l2 = log(arg);
   double mu = fn == FISHING_FN_MAY ? l2 : __dsub_rn(base, l2);       // base - (+0) = base for Allen and Ricker
   if (noisy) mu = __dadd_rn(mu, __dmul_rn(g.sigma, z));
-  const double v = exp(mu);
+  const double v = exp_tab(mu, GlobalTabs());
   return (0.0 > v) ? 0.0 : v;
 }
 

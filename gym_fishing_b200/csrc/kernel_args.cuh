@@ -11,6 +11,8 @@ namespace fishing {
 // internal launch flag (upper bits of StepArgs::flags, never part of the public fishing_flags): use programmatic
 // dependent launch for this step
 constexpr uint32_t STEP_FLAG_PDL = 1u << 16;
+// internal: phase A of K1 prefetches this thread's state lines into the L2 (set by the host when the state no longer fits there)
+constexpr uint32_t STEP_FLAG_PREFETCH = 1u << 17;
 
 struct StepArgs {
   int64_t n;          // environments in this launch

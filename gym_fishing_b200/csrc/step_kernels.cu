@@ -114,13 +114,11 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
   double2 z = make_double2(0.0, 0.0);
   if (live) {
     act = ld_stream(reinterpret_cast<const AT2*>(a.action) + j);
-    // Start pulling this thread's state lines towards the L2 now, so that phase B finds them close by instead of paying
-    // a full round trip after the wait (a second DRAM trip once the batch is past the L2 -- fishing-v4 carries 28 B of
-    // state per environment -- and the far-partition L2 latency below that).  The L2 is the coherence point, so a line
-    // prefetched before the previous launch has written it is still read correctly afterwards.  Measured on B200:
-    // fishing-v4 at 2^22 envs 7.94 -> 7.00 ms per 128 steps; fishing-v1 sigma = 0.01: 7.37 -> 6.89 us per launch at
-    // 2^20 envs, 60.4 -> 53.1 us at 2^23.  Without noise phase A is too short for the prefetch to pay for its issue slots.
-    if (PM == P_PERENV || noisy) {
+    // Start pulling this thread's state lines towards the L2 now, so that phase B finds them close by instead of paying a
+    // second DRAM trip after the wait.  Only when the per-launch state no longer fits in the L2 (the host sets the flag from
+    // n x bytes of state per environment, abi.cu): measured in round 2 (tools/k1_scaling.py, fishing-v1 / fishing-v4, sigma = 0.01)
+    // the prefetch costs 2 - 3 % while the state is L2-resident (2^20 .. 2^22 / 2^21 envs) and gains 1 - 4 % beyond.
+    if (a.flags & STEP_FLAG_PREFETCH) {
       prefetch_l2(reinterpret_cast<const double2*>(a.state_in) + j);
       prefetch_l2(reinterpret_cast<const int2*>(a.years) + j);
       if (PM == P_PERENV) {

@@ -273,3 +273,36 @@ def test_two_correction_quotient_is_correctly_rounded_in_exact_arithmetic():
     b = np.concatenate([b, ones, zeros, ones, ones[::-1]])
     bad = [(x, d) for x, d in zip(a.tolist(), b.tolist()) if div2(x, d) != x / d]
     assert not bad, bad[:5]
+
+
+def test_build_id_ties_the_library_to_the_tree_and_a_failed_build_is_loud(tmp_path, monkeypatch):
+    """The library carries a hash of the sources it was compiled from (fishing_build_id); the loader refuses one that was built
+    from other sources, a compile error raises instead of silently keeping yesterday's binary, and FISHING_ALLOW_STALE_LIB=1 is
+    the explicit way to keep it."""
+    import shutil
+
+    from gym_fishing_b200 import _native as nat
+    from gym_fishing_b200 import build as B
+
+    B.build()
+    assert B.library_id() == B.source_id() == nat.build_id() and len(nat.build_id()) == 16
+    assert not B.needs_build()
+    # a compile error: RuntimeError, even though an older library is sitting at the output path
+    out = str(tmp_path / "libselftest.so")
+    shutil.copy(B.OUT, out)
+    monkeypatch.delenv("FISHING_ALLOW_STALE_LIB", raising=False)
+    with pytest.raises(RuntimeError, match="nvcc failed"):
+        B.build(force=True, extra_flags=["-DFISHING_BUILD_SELFTEST_FAIL"], out=out, sources=("abi.cu",))   # the file that carries the #error
+    monkeypatch.setenv("FISHING_ALLOW_STALE_LIB", "1")
+    assert B.build(force=True, extra_flags=["-DFISHING_BUILD_SELFTEST_FAIL"], out=out, sources=("abi.cu",)) == out   # explicit opt-in keeps the old file
+    monkeypatch.delenv("FISHING_ALLOW_STALE_LIB")
+    # a library whose id differs from the tree is refused at load time
+    code = ("import gym_fishing_b200.build as B\n"
+            "B.source_id = lambda extra_flags=(): '0' * 16\n"
+            "from gym_fishing_b200 import _native as nat\n"
+            "try:\n    nat.lib()\nexcept ImportError as e:\n    print('REFUSED', 'other sources' in str(e))\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.pop("FISHING_B200_LIB", None)
+    env.pop("FISHING_ALLOW_STALE_LIB", None)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "REFUSED True" in res.stdout, res.stdout + res.stderr

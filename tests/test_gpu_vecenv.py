@@ -505,6 +505,13 @@ def test_wire_formats_packed_dones_and_float32_per_array():
     obs_b, _, done_b = ref.step_many(acts[:5])
     o1b, _, bits_b = pk.step_many(acts[:5])
     assert np.array_equal(o1b, obs_b) and np.array_equal(pk.unpack_dones(bits_b), done_b)
+    # a longer call than any before: the [T, n] staging blocks are re-allocated
+    more = rng.uniform(-1, 0.2, size=(2 * T + 3, n))
+    obs_c, rew_c, done_c = ref.step_many(more)
+    o1c, r1c, bits_c = pk.step_many(more)
+    assert bits_c.shape == (2 * T + 3, (n + 7) // 8) and np.array_equal(o1c, obs_c) and np.array_equal(r1c, rew_c)
+    assert np.array_equal(pk.unpack_dones(bits_c), done_c)
+    assert sb.step_many(more)[0].shape == (2 * T + 3, n)
     with pytest.raises(ValueError, match="even"):
         gf.FishingVecEnv("fishing-v1", num_envs=7, io="numpy", packed_done=True)
     for v in (ref, pk, sb):
