@@ -314,7 +314,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * per_proc * cores / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),      # the same dict as this run's GPU arm prints
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -740,7 +740,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
                     "lock_steps_timed": e2e_T, "host_cores_bound_to_gpu_numa_node": bound_cpus,
-                    "api": f"FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, {args.e2e_chunk} lock-steps per call: one strided H2D and three strided D2H copies per third of the batch)",
+                    "api": f"FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, {args.e2e_chunk} lock-steps per call: one strided H2D and three strided D2H copies per sixth of the batch)",
                     "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"},
                     "link_only": {"value": link_f64, "unit": UNIT,
                                   "what": "the same 8 B in / 17 B out per env-step as bare pinned-memory copies, both directions in flight, no kernels"},
