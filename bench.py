@@ -531,6 +531,8 @@ def run_gpu(args):
         fused_policy_leg(nat.V1, "escapement_in_kernel", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi1ELb0EE",
                          0.49960005283355713,      # float32 BMSY of the default logistic model (tests/golden/kat.json kat1.S)
                          29, True, False, **CFG)   # fishing-v1 step 22 + continuous escapement policy 6 + return accumulation 1
+        fused_policy_leg(nat.V1, "escapement_in_kernel_plain", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi0ELb0EE",
+                         0.49960005283355713, 29, False, False, **CFG)   # the same without auto-reset (the reference's plain loop)
         fused_policy_leg(nat.V2, "tipping_escapement_in_kernel", "rollout_fast_kernelILi1ELi0ELi1ELb1ELi2ELb0EE",
                          float.fromhex("0x1.9374bcp-1"), 31, False, True, r=0.3, K=1.0, C=0.5, sigma=0.05, x0=0.75, Tmax=1000)
     del obs, rew, done
@@ -740,7 +742,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 17,
                     "step_definition": "one lock-step of the n-env batch per GPU (actions f64 in; obs f64 + reward f64 + done u8 out)",
                     "lock_steps_timed": e2e_T, "host_cores_bound_to_gpu_numa_node": bound_cpus,
-                    "api": f"FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, {args.e2e_chunk} lock-steps per call: one strided H2D and three strided D2H copies per sixth of the batch)",
+                    "api": f"FishingVecEnv(io='numpy').step_many -> fishing_vec_step_many (actions/obs/reward/done in pinned host memory, {args.e2e_chunk} lock-steps per call: one strided H2D and three strided D2H copies per twelfth of the batch)",
                     "per_step_api": {"value": e2e_per_step, "unit": UNIT, "api": "FishingVecEnv(io='numpy').step -> fishing_vec_step, one call per lock-step"},
                     "link_only": {"value": link_f64, "unit": UNIT,
                                   "what": "the same 8 B in / 17 B out per env-step as bare pinned-memory copies, both directions in flight, no kernels"},

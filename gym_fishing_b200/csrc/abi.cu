@@ -759,12 +759,15 @@ static int vec_step_many_core(fishing_vec* v, int64_t T, const void* actions, in
   const bool obs32 = wire & FISHING_WIRE_OBS_F32, rew32 = wire & FISHING_WIRE_REWARD_F32, bits = wire & FISHING_WIRE_DONE_BITS;
   const size_t osz = obs32 ? 4 : 8, rsz = rew32 ? 4 : 8;
   const size_t host_bits_row = (size_t)(n + 7) / 8;
-  // six chunks over three streams by default: the first action block (nothing can overlap it) is a sixth of the batch
-  static const int64_t nchunks = [] {
+  // chunks rotate over three streams; the first action block (nothing can overlap it) is 1/chunks of the call's H2D traffic.
+  // Measured on B200 (tools/e2e_chunks.py, 2^20 envs, float64 wire): T = 8 per call 2.67 / 2.78 / 2.74 / 2.54e9 env-steps/s
+  // for 3 / 6 / 12 / 24 chunks, T = 32: 2.75 / 2.90 / 2.97 / 2.94e9.
+  static const int64_t forced = [] {
     const char* e = std::getenv("FISHING_VEC_MANY_CHUNKS");
-    const long c = e ? std::atol(e) : 6;
-    return (int64_t)((c >= 1 && c <= 64) ? c : 6);
+    const long c = e ? std::atol(e) : 0;
+    return (int64_t)((c >= 1 && c <= 64) ? c : 0);
   }();
+  const int64_t nchunks = forced ? forced : (T >= 16 ? 12 : 6);
   int64_t chunk = ((n + nchunks - 1) / nchunks + 1023) / 1024 * 1024;
   if (chunk > n) chunk = n;
   int rc = 0;
