@@ -3,7 +3,13 @@
 This is NOT part of the reference (which draws from numpy's global MT19937); it restates the *new* counter-based
 generator so that tests can check the CUDA implementation word for word: Philox4x32-10 (Salmon, Moraes, Dror, Shaw,
 "Parallel random numbers: as easy as 1, 2, 3", SC'11; known-answer vectors from the Random123 distribution's
-kat_vectors file are checked in tests/test_philox_ref.py), 52-bit open-interval uniforms and Box-Muller."""
+kat_vectors file are checked in tests/test_philox_ref.py), 52-bit open-interval uniforms and Box-Muller.
+
+This is the MATHEMATICAL definition of the draws (numpy's log / sqrt / cos / sin).  The device evaluates the same formulas
+with its own table-assisted routines (gym_fishing_b200/csrc/normal.cuh, round 2; round 1: fdlibm-style polynomials), so
+device draws agree with this file to a few ulps, not bit for bit (tests/test_gpu_parity.py:
+test_philox_normals_against_long_double_evaluation bounds the difference by 3e-15); parity tests of the dynamics therefore
+export the engine's own draws (fishing_noise_fill) and inject them here, never the other way round."""
 from __future__ import annotations
 
 import numpy as np
