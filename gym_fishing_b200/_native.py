@@ -87,6 +87,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.environ.get("FISHING_B200_LIB") and os.environ.get("FISHING_ALLOW_STALE_LIB") != "1":
+        # a library compiled from other sources than the tree holds is rebuilt here (nvcc is part of the image); if that
+        # fails the error is raised -- the engine never runs yesterday's kernels silently
+        from .build import build, needs_build
+
+        if needs_build():
+            build()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA engine is not built and gym_fishing_b200 has no CPU fallback. "

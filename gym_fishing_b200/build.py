@@ -67,6 +67,22 @@ def build(force=False, verbose=False, extra_flags=(), out=None, sources=SOURCES)
     out = out or OUT
     if not force and out == OUT and not needs_build():
         return OUT
+    import fcntl
+    from concurrent.futures import ThreadPoolExecutor
+
+    # one builder at a time (torchrun starts eight ranks that all find the same stale library); whoever waited re-checks
+    lock = open(out + ".lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and out == OUT and not needs_build():
+            return OUT
+        return _build_locked(verbose, extra_flags, out, sources)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose, extra_flags, out, sources):
     from concurrent.futures import ThreadPoolExecutor
 
     objdir = os.path.join(os.path.dirname(_HERE), "build", "obj_" + os.path.basename(out))

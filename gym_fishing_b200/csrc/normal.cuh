@@ -141,6 +141,11 @@ static __constant__ double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHI
                                        FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
                                        FISHING_PE2, FISHING_PE1, FISHING_PE0};
 #define FN_COEF(k) FN_C[k]
+// The high word of 1.0, read from the constant bank instead of being written as a literal: (w & 0xFFFFF) | 0x3FF00000 with two
+// literals is two LOP3 (one immediate per instruction), with the second operand in a register it is one -- and LOP3 sits on
+// the issue port that bounds the fused kernels.  Three of them per pair of draws.
+static __constant__ uint32_t FN_ONE_HI_C = 0x3FF00000u;
+#define FN_ONE_HI FN_ONE_HI_C
 
 struct GlobalTabs {
   __device__ __forceinline__ double exp_at(uint32_t byte_off) const {
@@ -189,6 +194,7 @@ static const double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, 
                                 FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
                                 FISHING_PE2, FISHING_PE1, FISHING_PE0};
 #define FN_COEF(k) FN_C[k]
+#define FN_ONE_HI 0x3FF00000u
 struct HostTabs {
   double exp_at(uint32_t byte_off) const { return h_exp_table[byte_off >> 3]; }
   double2 log_at(uint32_t byte_off) const { return h_normal_log_table[byte_off >> 4]; }
@@ -202,11 +208,12 @@ FN_HD Normal2 normal_from_words(const uint32_t (&w)[4], const Tabs& tb) {
   // ---- a = -2 ln u1
   // 52 random bits -> (k + 0.5) 2^-52 without an integer->double conversion: place the bits in the significand of a number
   // in [1, 2) and subtract 1 - 2^-53; the subtraction is exact and normalises the result.
-  const double u1 = sub(hilo(0x3FF00000u | (w[1] & 0xFFFFFu), w[0]), 0x1.fffffffffffffp-1);
+  const uint32_t one_hi = FN_ONE_HI;
+  const double u1 = sub(hilo(one_hi | (w[1] & 0xFFFFFu), w[0]), 0x1.fffffffffffffp-1);
   const uint32_t hi = hi32(u1);
   const uint32_t mant = hi & 0xFFFFFu;
   const double2 le = tb.log_at(((mant + 0x800u) >> 8) & 0x1FF0u);         // entry round(256 (m - 1)), 16 bytes each
-  const double m = hilo(0x3FF00000u | mant, lo32(u1));
+  const double m = hilo(one_hi | mant, lo32(u1));
   // e + adj: the addition carries into the exponent field exactly when the entry is one of those with c >= sqrt 2
   const int ep = (int)(hi + (0x00100000u - FISHING_LOG_THR) - 0x3FF00000u) >> 20;
   const double rr = fma_(m, le.x, 2.0);
@@ -225,7 +232,7 @@ FN_HD Normal2 normal_from_words(const uint32_t (&w)[4], const Tabs& tb) {
   const uint32_t mant2 = w[3] & 0xFFFFFu;
   const uint32_t t2 = mant2 + 0x800u;
   const double2 cs = tb.trig_at((t2 >> 8) & 0x1FF0u);                     // entry j = round(256 frac)
-  const double f = sub(hilo(0x3FF00000u | mant2, w[2]), hilo(0x3FF00000u + (t2 & 0x1FF000u), 0u));   // frac - j/256, exact
+  const double f = sub(hilo(one_hi | mant2, w[2]), hilo(0x3FF00000u + (t2 & 0x1FF000u), 0u));   // frac - j/256, exact
   const double f2 = mul(f, f);
   const double ps = fma_(fma_(FN_COEF(5), f2, FN_COEF(6)), f2, FN_COEF(7));
   const double pc = fma_(fma_(FN_COEF(8), f2, FN_COEF(9)), f2, FN_COEF(10));

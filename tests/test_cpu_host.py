@@ -296,13 +296,18 @@ def test_build_id_ties_the_library_to_the_tree_and_a_failed_build_is_loud(tmp_pa
     monkeypatch.setenv("FISHING_ALLOW_STALE_LIB", "1")
     assert B.build(force=True, extra_flags=["-DFISHING_BUILD_SELFTEST_FAIL"], out=out, sources=("abi.cu",)) == out   # explicit opt-in keeps the old file
     monkeypatch.delenv("FISHING_ALLOW_STALE_LIB")
-    # a library whose id differs from the tree is refused at load time
+    # a library whose id differs from the tree is never loaded as it is: the loader rebuilds it, and where that is impossible
+    # (here: no compiler) it raises
     code = ("import gym_fishing_b200.build as B\n"
             "B.source_id = lambda extra_flags=(): '0' * 16\n"
+            "B._nvcc = lambda: '/nonexistent/nvcc'\n"
             "from gym_fishing_b200 import _native as nat\n"
-            "try:\n    nat.lib()\nexcept ImportError as e:\n    print('REFUSED', 'other sources' in str(e))\n")
+            "try:\n    nat.lib()\n    print('LOADED')\nexcept RuntimeError as e:\n    print('REFUSED', 'nvcc failed' in str(e))\n")
     env = dict(os.environ, PYTHONPATH=ROOT)
     env.pop("FISHING_B200_LIB", None)
     env.pop("FISHING_ALLOW_STALE_LIB", None)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
-    assert "REFUSED True" in res.stdout, res.stdout + res.stderr
+    assert "REFUSED True" in res.stdout and "LOADED" not in res.stdout, res.stdout + res.stderr
+    env["FISHING_ALLOW_STALE_LIB"] = "1"          # the explicit opt-in loads it
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "LOADED" in res.stdout, res.stdout + res.stderr
