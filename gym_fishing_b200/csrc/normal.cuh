@@ -141,11 +141,15 @@ static __constant__ double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHI
                                        FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
                                        FISHING_PE2, FISHING_PE1, FISHING_PE0};
 #define FN_COEF(k) FN_C[k]
-// The high word of 1.0, read from the constant bank instead of being written as a literal: (w & 0xFFFFF) | 0x3FF00000 with two
-// literals is two LOP3 (one immediate per instruction), with the second operand in a register it is one -- and LOP3 sits on
-// the issue port that bounds the fused kernels.  Three of them per pair of draws.
+// The high word of 1.0 as a literal.  (Reading it from the constant bank turns (w & 0xFFFFF) | 0x3FF00000 into ONE LOP3 instead
+// of two -- tried in round 2, FISHING_AB_ONE_FROM_CONSTANT: one LOP3 less per pair-step, but 2 % slower fused kernels and a 15 %
+// slower trace kernel, the register allocation changes for the worse.)
 static __constant__ uint32_t FN_ONE_HI_C = 0x3FF00000u;
+#ifdef FISHING_AB_ONE_FROM_CONSTANT
 #define FN_ONE_HI FN_ONE_HI_C
+#else
+#define FN_ONE_HI 0x3FF00000u
+#endif
 
 struct GlobalTabs {
   __device__ __forceinline__ double exp_at(uint32_t byte_off) const {
