@@ -84,6 +84,20 @@ def tree_sum(parts):
     return parts[0]
 
 
+def tree_fold_rows(t):
+    """tree_sum over the rows of a 2-D tensor, level by level on whole slices (log2(rows) kernel launches instead of one per
+    row): t[0::2] + t[1::2] pairs adjacent rows exactly like tree_sum does, an odd last row is carried up unchanged."""
+    while t.shape[0] > 1:
+        even = t.shape[0] & ~1
+        nxt = t[0:even:2] + t[1:even:2]
+        if t.shape[0] & 1:
+            import torch
+
+            nxt = torch.cat([nxt, t[-1:]], dim=0)
+        t = nxt
+    return t[0]
+
+
 def allreduce_stats(stats, deterministic=True):
     """Combine per-rank statistics tensors (any shape, float64).  deterministic=True: all_gather + fixed pairwise tree
     in rank order (bit-identical for 1/2/4/8 GPUs); False: a plain NCCL/gloo all_reduce(SUM)."""

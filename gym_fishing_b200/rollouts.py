@@ -48,9 +48,9 @@ def rollout_stats(env_id, num_envs, T, *, policy="escapement", S=None, msy_q=Non
     groups = 256 if num_envs % (256 * world) == 0 else 1
     local = b.reduce_stats(out["ret"], out["done_step"], groups=groups)
     total = allreduce_stats(local, deterministic=deterministic)
-    from .distributed import tree_sum
+    from .distributed import tree_fold_rows
 
-    folded = tree_sum([total[i] for i in range(total.shape[0])]).unsqueeze(0)
+    folded = tree_fold_rows(total).unsqueeze(0)      # the 256 group columns, same adjacent-pair tree as on the device
     res = _finish(folded, num_envs)
     res = {k: (v[0] if hasattr(v, "shape") and v.ndim else v) for k, v in res.items()}
     if keep_per_env:

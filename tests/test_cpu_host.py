@@ -311,3 +311,16 @@ def test_build_id_ties_the_library_to_the_tree_and_a_failed_build_is_loud(tmp_pa
     env["FISHING_ALLOW_STALE_LIB"] = "1"          # the explicit opt-in loads it
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
     assert "LOADED" in res.stdout, res.stdout + res.stderr
+
+
+def test_tree_fold_rows_is_the_same_adjacent_pair_tree():
+    """rollout_stats folds its 256 group columns with whole-slice additions (8 launches) instead of 255 scalar ones; the order
+    of the floating-point additions -- hence every bit -- is that of distributed.tree_sum and of the device's K4 tree."""
+    import torch
+
+    from gym_fishing_b200.distributed import tree_fold_rows, tree_sum
+
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 2, 3, 5, 8, 255, 256, 257, 1000):
+        t = torch.randn(n, 3, dtype=torch.float64, generator=g) * 1e6
+        assert torch.equal(tree_sum([t[i] for i in range(n)]), tree_fold_rows(t)), n
