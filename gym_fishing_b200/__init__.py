@@ -7,7 +7,7 @@
 All dynamics run in hand-written sm_100a CUDA kernels (gym_fishing_b200/csrc) behind a C ABI
 (include/fishing_b200.h); importing the package never touches the GPU, using an environment without a CUDA device
 raises."""
-from . import spaces  # noqa: F401
+from . import shared_env, spaces  # noqa: F401
 from .registration import make, register, spec_ids  # noqa: F401
 from . import envs  # noqa: F401  (registers the ids)
 from .envs import BaseFishingEnv, FishingCtsEnv, FishingEnv, FishingModelError, FishingTippingEnv  # noqa: F401

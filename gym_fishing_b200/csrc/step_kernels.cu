@@ -496,6 +496,11 @@ static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
+#ifndef FISHING_K1_BS
+#define FISHING_K1_BS 256      // threads per block of the lock-step kernel (timing builds: 128 / 512)
+#endif
+constexpr int K1_BS = FISHING_K1_BS;
+
 template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
   constexpr bool CAN_LEAN = true;
@@ -503,13 +508,13 @@ static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
   const bool lean = CAN_LEAN && !extra && !a.noise && !a.reset_noise && !a.out_obs2 && !a.out_stock && !a.out_harvest && !a.out_terminal;
   if (vec) {
     const int64_t npairs = a.n >> 1;
-    const int64_t blocks = (npairs + 255) / 256;
+    const int64_t blocks = (npairs + K1_BS - 1) / K1_BS;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (a.flags & STEP_FLAG_PDL) {
       // programmatic dependent launch: this grid may start while the previous kernel in the stream is still draining
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)blocks);
-      cfg.blockDim = dim3(256);
+      cfg.blockDim = dim3(K1_BS);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
@@ -518,13 +523,13 @@ static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       count_launch();
-      if (lean) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, CAN_LEAN>, a);
-      if (extra) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, false, true>, a);
-      return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, 256, false>, a);
+      if (lean) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, K1_BS, CAN_LEAN>, a);
+      if (extra) return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, K1_BS, false, true>, a);
+      return cudaLaunchKernelEx(&cfg, step_kernel_vec2<GROWTH, PM, ACT, K1_BS, false>, a);
     }
-    if (lean) step_kernel_vec2<GROWTH, PM, ACT, 256, CAN_LEAN><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else if (extra) step_kernel_vec2<GROWTH, PM, ACT, 256, false, true><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else step_kernel_vec2<GROWTH, PM, ACT, 256, false><<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (lean) step_kernel_vec2<GROWTH, PM, ACT, K1_BS, CAN_LEAN><<<(unsigned)blocks, K1_BS, 0, st>>>(a);
+    else if (extra) step_kernel_vec2<GROWTH, PM, ACT, K1_BS, false, true><<<(unsigned)blocks, K1_BS, 0, st>>>(a);
+    else step_kernel_vec2<GROWTH, PM, ACT, K1_BS, false><<<(unsigned)blocks, K1_BS, 0, st>>>(a);
   } else {
     const int grid = grid_for(a.n, 256, 8);
     step_kernel_scalar<GROWTH, PM, ACT><<<grid, 256, 0, st>>>(a);

@@ -23,6 +23,7 @@ VARIANTS = {
     "mb10": ["-DFISHING_K2_MINBLOCKS=10"],                # ... 48 registers
     "unroll4": ["-DFISHING_K2_UNROLL=4"],
     "libexp": ["-DFISHING_AB_LIBEXP"],
+    "k1bs128": ["-DFISHING_K1_BS=128"], "k1bs512": ["-DFISHING_K1_BS=512"],   # block size of the lock-step kernel
     "one_from_constant": ["-DFISHING_AB_ONE_FROM_CONSTANT"],   # 1.0's high word from the constant bank (one LOP3 less per use)
     "v4nodraw": ["-DFISHING_AB_V4_NODRAW"],               # NOT the product: fishing-v4 resets without the Philox / Box-Muller work
     "v4nowrite": ["-DFISHING_AB_V4_NOWRITE"],             # NOT the product: ... without the scattered K / r rewrites                    # fishing-v2 with libdevice's exp instead of csrc/normal.cuh:exp_tab
