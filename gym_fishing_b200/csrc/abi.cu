@@ -757,7 +757,6 @@ static int vec_step_many_core(fishing_vec* v, int64_t T, const void* actions, in
   if (e != cudaSuccess) return (int)e;
   if (int rc = vec_ensure_staging(v, T, wire)) return rc;
   const bool obs32 = wire & FISHING_WIRE_OBS_F32, rew32 = wire & FISHING_WIRE_REWARD_F32, bits = wire & FISHING_WIRE_DONE_BITS;
-  const size_t osz = obs32 ? 4 : 8, rsz = rew32 ? 4 : 8;
   const size_t host_bits_row = (size_t)(n + 7) / 8;
   // chunks rotate over three streams; the first action block (nothing can overlap it) is 1/chunks of the call's H2D traffic.
   // Measured on B200 (tools/e2e_chunks.py, 2^20 envs, float64 wire): T = 8 per call 2.67 / 2.78 / 2.74 / 2.54e9 env-steps/s
@@ -829,7 +828,6 @@ static int vec_step_many_core(fishing_vec* v, int64_t T, const void* actions, in
                                    cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) rc = (int)e;
     bit_words_before += words;
-    (void)osz; (void)rsz;
   }
   for (int i = 0; i < 3; ++i) {
     e = cudaStreamSynchronize(v->streams[i]);
