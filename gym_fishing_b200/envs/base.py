@@ -130,12 +130,22 @@ class BaseFishingEnv(_EnvBase):
         return isinstance(self.action_space, Discrete)
 
     def _fparams(self, **over):
-        kw = dict(r=self.r, K=self.K, sigma=self.sigma, C_=getattr(self, "C", 0.5), x0=self.init_state, Tmax=self.Tmax,
-                  n_actions=getattr(self, "n_actions", 100), sigma_p=getattr(self, "sigma_p", 0.1), seed=self._seed)
-        if self._kind == nat.V4:
-            kw["r"], kw["K"] = self.r_mean, self.K_mean
+        """The parameter block for the next launch, from the attributes as they are NOW (callers mutate them between steps,
+        like the reference's callers do).  The ctypes structure is rebuilt only when one of them changed: building it costs
+        about as much as the kernel launch itself."""
+        v4 = self._kind == nat.V4
+        key = (self.r_mean if v4 else self.r, self.K_mean if v4 else self.K, self.sigma, getattr(self, "C", 0.5), self.init_state,
+               self.Tmax, getattr(self, "n_actions", 100), getattr(self, "sigma_p", 0.1), self._seed)
+        if not over:
+            cached = getattr(self, "_p_cache", None)
+            if cached is not None and cached[0] == key:
+                return cached[1]
+        kw = dict(zip(("r", "K", "sigma", "C_", "x0", "Tmax", "n_actions", "sigma_p", "seed"), key))
         kw.update(over)
-        return nat.make_params(self._kind, **kw)
+        p = nat.make_params(self._kind, **kw)
+        if not over:
+            self._p_cache = (key, p)
+        return p
 
     def _soa(self):
         s = self._slot
