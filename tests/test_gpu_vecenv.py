@@ -676,3 +676,45 @@ def test_env_simulate_runs_on_the_device_with_the_reference_use_of_numpys_genera
             return np.array([-0.9]), None
     host_df = env.simulate(Const(), reps=2)
     assert 2 <= len(host_df) <= 100 and set(host_df.rep) == {0, 1} and (host_df.action.iloc[1:5] > 0).all()
+
+
+@pytest.mark.parametrize("env_id,kw", [("fishing-v0", dict(sigma=0.05, Tmax=6)), ("fishing-v2", dict(sigma=0.05, Tmax=6)),
+                                       ("fishing-v4", dict(sigma=0.05, Tmax=6)), ("fishing-v11", dict(Tmax=6)),
+                                       ("fishing-v1", dict(sigma=0.05, Tmax=6, K=2.0))])
+def test_extra_outputs_of_the_step_kernel_for_every_family(env_id, kw):
+    """monitor= / sb3_dtypes= (the EXTRA instantiation of K1, fishing_step_ex) against the plain environment: same trajectories,
+    float32 values are the casts, episode statistics equal the sums / counts taken from the plain run -- for the Discrete, the
+    tipping-point, the per-environment-parameter, the model-uncertainty and the general-K kernels, with an environment count that
+    leaves a partial last warp."""
+    import torch
+
+    import gym_fishing_b200 as gf
+
+    n, T = 1000 + 38, 30
+    g = torch.Generator(device="cuda").manual_seed(5)
+    plain = gf.FishingVecEnv(env_id, num_envs=n, seed=21, **kw)
+    extra = gf.FishingVecEnv(env_id, num_envs=n, seed=21, monitor=True, sb3_dtypes=True, **kw)
+    o0, o1 = plain.reset(), extra.reset()
+    assert o1.dtype == torch.float32 and torch.equal(o1, o0.float())
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    length = torch.zeros(n, dtype=torch.int64, device="cuda")
+    episodes = 0
+    for t in range(T):
+        if env_id == "fishing-v0":
+            a = torch.randint(0, 40, (n, 1), device="cuda", generator=g)
+        else:
+            a = torch.rand(n, 1, dtype=torch.float64, device="cuda", generator=g) * 0.7 - 1.0
+        o, r, d, _ = plain.step(a)
+        o32, r32, d2, infos = extra.step(a)
+        assert torch.equal(d, d2) and torch.equal(o32, o.float()) and torch.equal(r32, r.float())
+        assert torch.equal(extra.batch.state, plain.batch.state)              # the float64 state itself is untouched
+        ret += r
+        length += 1
+        idx, er, el = infos.episode_arrays()
+        assert np.array_equal(idx, d.nonzero().reshape(-1).cpu().numpy())
+        assert np.array_equal(er, ret[d].cpu().numpy()) and np.array_equal(el, length[d].cpu().numpy())
+        episodes += len(idx)
+        ret[d] = 0
+        length[d] = 0
+    assert episodes > n
+    plain.close(), extra.close()
