@@ -24,7 +24,11 @@
 
 namespace fishing {
 
-constexpr int K2_UNROLL = FISHING_K2_UNROLL;   // timing builds may unroll the fused loop (tools/ab_build.py)
+constexpr int K2_UNROLL = FISHING_K2_UNROLL;
+#ifndef FISHING_SWEEP_UNROLL
+#define FISHING_SWEEP_UNROLL 4
+#endif
+constexpr int SWEEP_UNROLL = FISHING_SWEEP_UNROLL;   // inner loop of the warp-cooperative sweep kernel   // timing builds may unroll the fused loop (tools/ab_build.py)
 
 // FISHING_GENERIC_ROLLOUT=1 forces the generic K2 kernel (A/B checks of the fast path)
 static bool generic_only() {
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
     if (NOISY && t0 + lane < T)
       d = normal_pair_keys(a.keys, noise_pair, a.step0 + (uint64_t)(t0 + lane), FISHING_STREAM_STEP, tb);
     const int nt = (T - t0 < 32) ? T - t0 : 32;
-#pragma unroll 1
+#pragma unroll SWEEP_UNROLL
     for (int dt = 0; dt < nt; ++dt) {
       double z0 = 0.0, z1 = 0.0;
       if (NOISY) {
@@ -701,11 +705,10 @@ __global__ void __launch_bounds__(128) rollout_sweep_warp_kernel(const RolloutAr
         fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e0, 0.0, z0, t, gid0, tb);
       if (MODE != M_FREEZE || !e1.frozen)
         fast_env_step<GROWTH, PM, FISHING_POLICY_ESCAPEMENT, NOISY, MODE>(a, e1, 0.0, z1, t, gid1, tb);
-      if (MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen)) {   // warp-uniform: the shuffles need every lane
-        all_done = true;
-        break;
-      }
     }
+    // warp-uniform exit (the shuffles need every lane): looked at once per block of 32 steps -- frozen environments skip
+    // their steps anyway, the vote only saves the rest of the walk when the whole warp is extinct
+    if (MODE == M_FREEZE && __all_sync(full, e0.frozen && e1.frozen)) all_done = true;
   }
   a.state[i0] = e0.s; a.state[i1] = e1.s;
   a.years[i0] = e0.years; a.years[i1] = e1.years;
