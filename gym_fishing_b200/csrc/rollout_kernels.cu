@@ -327,6 +327,22 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 //   * the return is accumulated unconditionally; when later episodes must not count (plain mode) its value at the first
 //     `done` is kept aside, which costs one select less than gating the addition.
 // Results are bit-identical to the generic kernel (tests/test_gpu_parity.py runs both against the oracle).
+// A/B (tools/ab_build.py imad_select): float64 selects of the fast path done as b + m (a - b) on the integer halves, m = 0 / 1
+// -- IADD / IMAD instead of two FSEL, which share the issue port of the FP64 pipe.
+#ifdef FISHING_AB_IMAD_SELECT
+__device__ __forceinline__ double sel64(bool p, double a, double b) {   // p ? a : b
+  const unsigned m = p ? 1u : 0u;
+  const unsigned alo = (unsigned)__double2loint(a), ahi = (unsigned)__double2hiint(a);
+  const unsigned blo = (unsigned)__double2loint(b), bhi = (unsigned)__double2hiint(b);
+  unsigned lo, hi;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(m), "r"(alo - blo), "r"(blo));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(m), "r"(ahi - bhi), "r"(bhi));
+  return __hiloint2double((int)hi, (int)lo);
+}
+#else
+__device__ __forceinline__ double sel64(bool p, double a, double b) { return p ? a : b; }
+#endif
+
 struct FastEnv {
   double s, K, r, S, ret, ret_snap, quota_const;
   int years, done_step;
@@ -358,9 +374,10 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
   double quota;
   if (POLICY == FISHING_POLICY_ESCAPEMENT) {
-    const double q = py_max(__dsub_rn(x, e.S), 0.0);            // policies.py:29
+    const double xs = __dsub_rn(x, e.S);
+    const double q = sel64(0.0 > xs, 0.0, xs);                   // max(x - S, 0.0), policies.py:29
     double act = action_cts<PM>(q, e.K, a.kd);                   // get_action, base_fishing_env.py:156
-    act = (act > 1.0) ? 1.0 : act;                               // np.clip: the lower bound cannot fire (act >= -1)
+    act = sel64(act > 1.0, 1.0, act);                            // np.clip: the lower bound cannot fire (act >= -1)
     quota = __dadd_rn(act, 1.0);
     if (PM != P_KONE) quota = __dmul_rn(quota, e.K);
   } else if (POLICY == FISHING_POLICY_MSY) {
@@ -368,7 +385,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   } else {
     quota = quota_f64<PM>(action, e.K);
   }
-  const double h = py_min(x, quota);
+  const double h = sel64(quota < x, quota, x);                   // min(x, quota), harvest_draw
   const double x1 = __dsub_rn(x, h);                             // == max(x - h, 0.0)
   const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, e.K, a.kd) : div_z(x1, e.K));
   const double room = __dsub_rn(1.0, frac);
@@ -384,7 +401,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
     g = __dmul_rn(x1, exp_tab(ex, tb));
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
-  const double x2 = alive ? g : 0.0;
+  const double x2 = sel64(alive, g, 0.0);
   const double s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, e.K, a.kd) : div_z(x2, e.K)), 1.0);
   const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
   e.years += 1;
