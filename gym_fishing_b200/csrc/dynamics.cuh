@@ -170,26 +170,42 @@ __device__ __forceinline__ double grow(double x1, double r, double K, double C, 
   }
 }
 
-// mu(x) of the five growth functions, growth_models.py:208-261, in the reference's evaluation order; log / pow / exp are
-// libdevice's (<= 1-2 ulp from numpy's), everything else one IEEE operation per reference operation.
+// mu(x) of the five growth functions, growth_models.py:208-261, in the reference's evaluation order.  log and exp are the
+// table-assisted ones of csrc/normal.cuh (log_tab: <= 2.1 ulp, exp_tab: <= 1.02 ulp; numpy's own are within 1 ulp), the powers
+// x^q / x^theta are exp(q log x) (x >= +0 or NaN here; a few ulps from numpy's power for the |q log x| < 10 of these models):
+// the family's parity is the 1e-12 tolerance of fishing-v2.  -DFISHING_AB_LIBLOG: libdevice's log / pow (round 1).  Everything
+// else is one IEEE operation per reference operation.
+#ifdef FISHING_AB_LIBLOG
+__device__ __forceinline__ double ln_(double x) { return log(x); }
+__device__ __forceinline__ double pow_ln(double x, double lx, double p) { (void)lx; return pow(x, p); }
+#else
+__device__ __forceinline__ double ln_(double x) { return log_tab(x, GlobalTabs()); }
+// x^p given lx = log(x), x >= +0 or NaN.  0 * inf would be NaN where numpy's power(x, 0) is 1 for every x
+__device__ __forceinline__ double pow_ln(double x, double lx, double p) {
+  (void)x;
+  return p == 0.0 ? 1.0 : exp_tab(__dmul_rn(p, lx), GlobalTabs());
+}
+#endif
+
 template <int FN>
 __device__ __forceinline__ double lognormal_mu(double x, const GrowthP& g) {
   if (FN == FISHING_FN_ALLEN) {            // np.log(x) + r * (1 - x / K) * (1 - C) / K
     const double y = div_u(__dmul_rn(__dmul_rn(g.r, __dsub_rn(1.0, div_u(x, g.K))), g.omC), g.K);
-    return __dadd_rn(log(x), y);
+    return __dadd_rn(ln_(x), y);
   } else if (FN == FISHING_FN_BEVERTON_HOLT) {   // log(A) + log(x) - log(1 + x / B), A = r + 1, B = K / r
     const double xc = (x < 0.0) ? 0.0 : x;                       // np.clip(x, 0, inf)
-    return __dsub_rn(__dadd_rn(g.logA, log(xc)), log(__dadd_rn(1.0, div_z(xc, g.B))));
+    return __dsub_rn(__dadd_rn(g.logA, ln_(xc)), ln_(__dadd_rn(1.0, div_z(xc, g.B))));
   } else if (FN == FISHING_FN_MAY) {       // x + x*r*(1 - x/M) - a*x^q / (x^q + b^q), then log
-    const double xq = pow(x, g.q);
+    const double xq = pow_ln(x, ln_(x), g.q);
     const double e = __dsub_rn(__dadd_rn(x, __dmul_rn(__dmul_rn(x, g.r), __dsub_rn(1.0, div_z(x, g.M)))),
                                div_z(__dmul_rn(g.a, xq), __dadd_rn(xq, g.bq)));
-    return log(e);
+    return ln_(e);
   } else if (FN == FISHING_FN_MYERS) {     // log(r + 1) + theta*log(x) - log(1 + x^theta / M)
-    return __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, log(x))),
-                     log(__dadd_rn(1.0, div_u(pow(x, g.theta), g.M))));
+    const double lx = ln_(x);
+    return __dsub_rn(__dadd_rn(g.logA, __dmul_rn(g.theta, lx)),
+                     ln_(__dadd_rn(1.0, div_u(pow_ln(x, lx, g.theta), g.M))));
   } else {                                 // Ricker: log(x) + r * (1 - x / K)
-    return __dadd_rn(log(x), __dmul_rn(g.r, __dsub_rn(1.0, div_u(x, g.K))));
+    return __dadd_rn(ln_(x), __dmul_rn(g.r, __dsub_rn(1.0, div_u(x, g.K))));
   }
 }
 
@@ -211,9 +227,9 @@ __device__ __forceinline__ double grow_lognormal(double x1, const GrowthP& g, do
 // lognormal_mu<FN> except for the power (pow(x, p) there, exp(p log x) here: a few ulps apart, the family's parity is a
 // 1e-12 tolerance).
 __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP& g, double z, bool noisy) {
-  const double lx = log(x1);    // x1 >= +0 or NaN here, so Beverton-Holt's np.clip(x, 0, inf) is the identity
+  const double lx = ln_(x1);    // x1 >= +0 or NaN here, so Beverton-Holt's np.clip(x, 0, inf) is the identity
   const bool has_pow = fn == FISHING_FN_MYERS || fn == FISHING_FN_MAY;
-  const double pw = exp_tab(__dmul_rn(fn == FISHING_FN_MYERS ? g.theta : g.q, lx), GlobalTabs());   // x^theta / x^q (unused otherwise)
+  const double pw = pow_ln(x1, lx, fn == FISHING_FN_MYERS ? g.theta : g.q);   // x^theta / x^q (unused otherwise)
   double base = 0.0, arg = 1.0;
   switch (fn) {
     case FISHING_FN_ALLEN:           // np.log(x) + r * (1 - x / K) * (1 - C) / K
@@ -236,7 +252,7 @@ __device__ __forceinline__ double grow_by_model(int fn, double x1, const GrowthP
       break;
   }
   (void)has_pow;
-  const double l2 = log(arg);
+  const double l2 = ln_(arg);
   double mu = fn == FISHING_FN_MAY ? l2 : __dsub_rn(base, l2);       // base - (+0) = base for Allen and Ricker
   if (noisy) mu = __dadd_rn(mu, __dmul_rn(g.sigma, z));
   const double v = exp_tab(mu, GlobalTabs());

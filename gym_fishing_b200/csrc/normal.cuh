@@ -282,4 +282,41 @@ FN_HD double exp_tab(double x, const Tabs& tb) {
   return mul(mul(y, hilo((uint32_t)(m1 + 1023) << 20, 0u)), hilo((uint32_t)(m2 + 1023) << 20, 0u));
 }
 
+// log(x) for the log-normal growth family (fishing-v5..v11, growth_models.py:208-261), from the Box-Muller's own log table:
+// x = 2^e m, entry i = round(256 (m - 1)), ln x = -((e + adj_i)(-2 ln 2) + T_i + rr + rr^2 Q(rr)) / 2 -- the expression
+// normal_from_words() evaluates for -2 ln u1, for any positive x.  T_0 = T_256 = 0 and e + adj = 0 around x = 1, so nothing
+// cancels there.  Mean 0.45 ulp, worst 2.1 ulp over all binades; for |ln x| < 2^-6 the cubic's truncation error (2^-58.6 = 2e-18
+// absolute, up to 6 ulp of so small a result) is what is left -- the growth functions pass mu = log(x) + ... through exp, so
+// it is the absolute error that counts (tools/normal_accuracy.cpp).  11 FP64 instructions and one 16-byte table load against
+// libdevice's ~35.  Zero, subnormal, negative, infinite and NaN arguments
+// leave through a rarely taken branch (an extinct stock, x = 0, is the one that occurs: -inf, as numpy).
+template <class Tabs>
+FN_HD double log_tab(double x, const Tabs& tb) {
+  using namespace nrm;
+  uint32_t hi = hi32(x), lo = lo32(x);
+  int ebias = 0;
+  if (hi - 0x00100000u >= 0x7FE00000u) {                   // not a positive normal number
+    if (x != x) return add(x, x);
+    if (x == 0.0) return -hilo(0x7FF00000u, 0u);          // log(+-0) = -inf
+    if (x < 0.0) return hilo(0x7FF80000u, 0u);            // log(negative) = NaN
+    if (hi == 0x7FF00000u) return x;                       // +inf
+    const double xs = mul(x, 0x1p54);                      // subnormal
+    hi = hi32(xs);
+    lo = lo32(xs);
+    ebias = -54;
+  }
+  const uint32_t mant = hi & 0xFFFFFu;
+  const double2 le = tb.log_at(((mant + 0x800u) >> 8) & 0x1FF0u);
+  const double m = hilo(FN_ONE_HI | mant, lo);
+  const int ep = ((int)(hi + (0x00100000u - FISHING_LOG_THR) - 0x3FF00000u) >> 20) + ebias;
+  const double rr = fma_(m, le.x, 2.0);
+  const double rr2 = mul(rr, rr);
+  double q = fma_(FN_COEF(0), rr, FN_COEF(1));
+  q = fma_(q, rr, FN_COEF(2));
+  q = fma_(q, rr, FN_COEF(3));
+  const double a0 = fma_(i2d(ep), FN_COEF(4), le.y);
+  const double a = fma_(rr2, q, add(a0, rr));
+  return fma_(a, -0.5, 0.0);                               // + 0.0: log(1) is +0, not -0
+}
+
 }  // namespace fishing

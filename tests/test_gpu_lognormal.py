@@ -1,6 +1,6 @@
 """"Next row" f1: fishing-v5..v11, the log-normal growth family of
-gym_fishing/envs/growth_models.py, through the same C-ABI step / rollout entry points.  log / pow / exp are libdevice's
-on the GPU and numpy's in the reference (<= 1-2 ulp apart), so parity is |a-b| <= 1e-12*max(|b|, K) like fishing-v2;
+gym_fishing/envs/growth_models.py, through the same C-ABI step / rollout entry points.  log / exp are the engine's table-assisted ones
+(csrc/normal.cuh, powers as exp(q log x)) and numpy's in the reference (a few ulp apart), so parity is |a-b| <= 1e-12*max(|b|, K) like fishing-v2;
 done flags exact."""
 import os
 

@@ -23,6 +23,7 @@ VARIANTS = {
     "mb10": ["-DFISHING_K2_MINBLOCKS=10"],                # ... 48 registers
     "unroll4": ["-DFISHING_K2_UNROLL=4"],
     "libexp": ["-DFISHING_AB_LIBEXP"],
+    "liblog": ["-DFISHING_AB_LIBLOG"],                     # fishing-v5..v11 with libdevice's log / pow instead of csrc/normal.cuh:log_tab
     "imad_select": ["-DFISHING_AB_IMAD_SELECT"],
     "sweep_unroll1": ["-DFISHING_SWEEP_UNROLL=1"], "sweep_unroll2": ["-DFISHING_SWEEP_UNROLL=2"], "sweep_unroll8": ["-DFISHING_SWEEP_UNROLL=8"],
     "k1bs128": ["-DFISHING_K1_BS=128"], "k1bs512": ["-DFISHING_K1_BS=512"],   # block size of the lock-step kernel

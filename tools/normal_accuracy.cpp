@@ -21,10 +21,11 @@ static uint64_t splitmix() {
 struct Stats {
   double max_abs = 0, sum_ulp = 0, max_ulp = 0;
   long n = 0, exact = 0;
-  void add(double got, long double ref) {
+  void add(double got, long double ref, double floor = 0.0) {     // floor: measure in ulps of max(|ref|, floor)
     const double r = (double)ref;
     const double err = std::fabs((double)((long double)got - ref));
-    const double ulp = std::fabs(std::nextafter(r, INFINITY) - r);
+    const double at = std::fabs(r) < floor ? floor : r;
+    const double ulp = std::fabs(std::nextafter(at, INFINITY) - at);
     if (err > max_abs) max_abs = err;
     sum_ulp += err / ulp;
     if (err / ulp > max_ulp) max_ulp = err / ulp;
@@ -90,6 +91,39 @@ int main(int argc, char** argv) {
   if (!std::isnan(fishing::exp_tab(NAN, fishing::HostTabs()))) return 2;
   printf("exp   : n=%ld  mean=%.3f ulp  max=%.2f ulp  correctly rounded %.1f%%\n", ex.n, ex.sum_ulp / ex.n, ex.max_ulp, 100.0 * ex.exact / ex.n);
   if (ex.max_ulp > 1.1) return 3;
+  // log_tab against logl: every binade in turn (the exponent term grows with |e|), around 1 (no cancellation allowed), cell
+  // boundaries of the table, subnormals, and the special values
+  Stats lg, lg1;
+  for (long i = 0; i < N; ++i) {
+    const double m = 1.0 + (double)(splitmix() >> 12) * 0x1p-52;
+    const int e = (int)(splitmix() % 2046) - 1022;
+    const double x = ldexp(m, i % 3 == 0 ? e : (int)(splitmix() % 12) - 6);
+    lg.add(fishing::log_tab(x, fishing::HostTabs()), logl((long double)x), 0x1p-6);
+    const double y = 1.0 + ((double)(splitmix() >> 11) * 0x1p-53 - 0.5) * (i % 2 ? 0x1p-6 : 0x1p-30);
+    lg1.add(fishing::log_tab(y, fishing::HostTabs()), logl((long double)y));
+  }
+  for (int i = 0; i <= 256; ++i)
+    for (int d = -2; d <= 2; ++d)
+      for (int e : {-1022, -60, -1, 0, 1, 7, 1023}) {
+        double x = ldexp(1.0 + (i - 0.5) / 256.0 < 1.0 ? 1.0 : 1.0 + (i - 0.5) / 256.0, e);
+        for (int k = 0; k < (d < 0 ? -d : d); ++k) x = std::nextafter(x, d < 0 ? 0.0 : INFINITY);
+        lg.add(fishing::log_tab(x, fishing::HostTabs()), logl((long double)x), 0x1p-6);
+      }
+  for (double x : {5e-324, 1e-310, 2.2250738585072009e-308, 2.2250738585072014e-308, 1.7976931348623157e308})
+    lg.add(fishing::log_tab(x, fishing::HostTabs()), logl((long double)x), 0x1p-6);
+  {
+    const fishing::HostTabs ht;
+    if (fishing::log_tab(1.0, ht) != 0.0 || std::signbit(fishing::log_tab(1.0, ht))) return 4;
+    if (fishing::log_tab(0.0, ht) != -(double)INFINITY || fishing::log_tab(-0.0, ht) != -(double)INFINITY) return 4;
+    if (fishing::log_tab((double)INFINITY, ht) != (double)INFINITY) return 4;
+    if (!std::isnan(fishing::log_tab(-1.0, ht)) || !std::isnan(fishing::log_tab(NAN, ht)) || !std::isnan(fishing::log_tab(-(double)INFINITY, ht))) return 4;
+  }
+  printf("log   : n=%ld  mean=%.3f ulp  max=%.2f ulp  correctly rounded %.1f%%\n", lg.n, lg.sum_ulp / lg.n, lg.max_ulp, 100.0 * lg.exact / lg.n);
+  printf("log~1 : n=%ld  max|err|=%.3e  mean=%.3f ulp  max=%.2f ulp  correctly rounded %.1f%%\n", lg1.n, lg1.max_abs, lg1.sum_ulp / lg1.n, lg1.max_ulp,
+         100.0 * lg1.exact / lg1.n);
+  // what the growth functions need is the ABSOLUTE error of mu = log(x) + ... (it goes through exp): <= 2.5 ulp of max(|result|, 2^-6)
+  // (`log`), and a few 1e-18 (the cubic's truncation error at the cell edges, 2^-58.6) where the result is small
+  if (lg.max_ulp > 2.5 || lg1.max_abs > 4e-18) return 5;
   for (const auto* s : {&rnd, &edge})
     printf("%s: n=%ld  max|err|=%.3e  mean=%.3f ulp  max=%.2f ulp  correctly rounded %.1f%%\n", s == &rnd ? "random" : "edges ", s->n,
            s->max_abs, s->sum_ulp / s->n, s->max_ulp, 100.0 * s->exact / s->n);
