@@ -37,6 +37,7 @@ EXPORTS = (
     "fishing_host_free", "fishing_vec_soa", "fishing_population_draw", "fishing_step_many", "fishing_vec_fetch_terminal", "fishing_vec_step_many",
     "fishing_reset_models", "fishing_population_draw_ln", "fishing_vec_step_many_f32", "fishing_probe_fp64", "fishing_step_ex",
     "fishing_vec_step_many_wire", "fishing_vec_fetch_array", "fishing_vec_store_array", "fishing_vec_set_params",
+    "fishing_probe_math",
 )
 
 
@@ -109,6 +110,8 @@ def lib():
     L.fishing_launch_count.argtypes = []
     L.fishing_probe_fp64.restype = C.c_int
     L.fishing_probe_fp64.argtypes = [vp, i32, i32, vp]
+    L.fishing_probe_math.restype = C.c_int
+    L.fishing_probe_math.argtypes = [i32, i64, vp, vp, vp]
     L.fishing_reset.restype = C.c_int
     L.fishing_reset.argtypes = [P, i64, i64, u64, vp, vp, FishingSoA, vp, vp]
     L.fishing_reset_models.restype = C.c_int

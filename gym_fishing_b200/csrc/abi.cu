@@ -193,6 +193,12 @@ int fishing_probe_fp64(double* scratch, int32_t blocks, int32_t iters, void* str
   return (int)launch_fp64_probe(scratch, blocks, iters, (cudaStream_t)stream);
 }
 
+int fishing_probe_math(int32_t fn, int64_t n, const double* x, double* out, void* stream) {
+  if (n < 0 || (fn != 0 && fn != 1) || (n > 0 && (!x || !out))) return FISHING_E_ARG;
+  if (n == 0) return 0;
+  return (int)launch_math_probe(fn, n, x, out, (cudaStream_t)stream);
+}
+
 const char* fishing_error_string(int code) {
   switch (code) {
     case 0: return "ok";

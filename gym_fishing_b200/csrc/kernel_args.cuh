@@ -119,6 +119,7 @@ cudaError_t launch_growth(int kind, int64_t n, const void* x, bool f32, double r
 cudaError_t launch_growth_ln(int fn, int64_t n, const double* x, const GrowthP& gp, bool derive_on_device, const double* z,
                              double* out, cudaStream_t st);
 cudaError_t launch_fp64_probe(double* scratch, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_math_probe(int fn, int64_t n, const double* x, double* out, cudaStream_t st);
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st);
 cudaError_t launch_rollout(const RolloutArgs& a, int kind, int policy, cudaStream_t st);
 int64_t reduce_scratch_doubles(int64_t n, int64_t groups);

@@ -646,6 +646,21 @@ cudaError_t launch_fp64_probe(double* scratch, int blocks, int iters, cudaStream
   return cudaGetLastError();
 }
 
+// The table-assisted log / exp of csrc/normal.cuh evaluated over an array (test aid: tests/test_gpu_lognormal.py compares the
+// device's results with numpy's and with the host build of the same header).
+__global__ void __launch_bounds__(256) math_probe_kernel(int fn, int64_t n, const double* __restrict__ x, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = fn == 0 ? log_tab(x[i], GlobalTabs()) : exp_tab(x[i], GlobalTabs());
+}
+
+cudaError_t launch_math_probe(int fn, int64_t n, const double* x, double* out, cudaStream_t st) {
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  math_probe_kernel<<<blocks, 256, 0, st>>>(fn, n, x, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bmsy(int kind, double r, double K, double C, bool f64, double* out_dev, cudaStream_t st) {
   if (f64) bmsy_kernel<double><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);
   else bmsy_kernel<float><<<1, 1024, 0, st>>>(kind, r, K, C, out_dev);

@@ -147,6 +147,12 @@ uint64_t fishing_launch_count(void);
  * `scratch` is a device array of >= 256 doubles (never written in practice).
  */
 int fishing_probe_fp64(double* scratch, int32_t blocks, int32_t iters, void* stream);
+/*
+ * Test aid: out[i] = f(x[i]) for the engine's own table-assisted float64 functions (csrc/normal.cuh), which stand where the
+ * reference calls numpy: fn = 0 log (np.log in growth_models.py:208-261), fn = 1 exp (np.exp in fishing_tipping_env.py:31,
+ * np.random.lognormal in growth_models.py).  x, out: device arrays of n doubles.
+ */
+int fishing_probe_math(int32_t fn, int64_t n, const double* x, double* out, void* stream);
 
 /*
  * reset -- BaseFishingEnv.reset (base_fishing_env.py:83-91), FishingModelError.reset / __init__ draws

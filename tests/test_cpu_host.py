@@ -324,3 +324,15 @@ def test_tree_fold_rows_is_the_same_adjacent_pair_tree():
     for n in (1, 2, 3, 5, 8, 255, 256, 257, 1000):
         t = torch.randn(n, 3, dtype=torch.float64, generator=g) * 1e6
         assert torch.equal(tree_sum([t[i] for i in range(n)]), tree_fold_rows(t)), n
+
+
+def test_table_assisted_normal_log_exp_host_build_against_long_double(tmp_path):
+    """tools/normal_accuracy.cpp compiles csrc/normal.cuh for the host (the same source the kernels compile) and checks the
+    Box-Muller, exp_tab and log_tab against 80-bit long double evaluation; its exit status carries the bounds
+    (draws < 3e-15 absolute, exp <= 1.1 ulp, log <= 2.5 ulp of max(|result|, 2^-6))."""
+    exe = str(tmp_path / "normal_accuracy")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "gym_fishing_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tools", "normal_accuracy.cpp")], check=True)
+    r = subprocess.run([exe, "400000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "log   :" in r.stdout and "exp   :" in r.stdout

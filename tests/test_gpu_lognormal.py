@@ -222,3 +222,61 @@ def test_policies_on_the_lognormal_family():
         assert abs(float(pol.msy) - q_ref) <= 1e-5 * abs(q_ref), (row["env"], float(pol.msy), q_ref)
         df = env.simulate(gf.escapement(env))
         assert len(df) == env.Tmax and df.reward.sum() > 0
+
+
+def _ulps(got, want, floor=0.0):
+    at = np.maximum(np.abs(want), floor)
+    return np.abs(got - want) / np.spacing(at)
+
+
+def test_table_assisted_log_and_exp_on_the_device_against_numpy():
+    """csrc/normal.cuh:log_tab / exp_tab as the kernels evaluate them (fishing_probe_math) against numpy's log / exp, which are
+    within 1 ulp of the truth: every binade, the neighbourhood of 1, table-cell boundaries, subnormals and the special values.
+    tools/normal_accuracy.cpp (run by tests/test_cpu_host.py) checks the host build of the same header against long double."""
+    import torch
+
+    from gym_fishing_b200 import _native as nat
+
+    def probe(fn, x):
+        xd = torch.as_tensor(x, device="cuda")
+        out = torch.empty_like(xd)
+        nat.check(nat.lib().fishing_probe_math(fn, xd.numel(), xd.data_ptr(), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "fishing_probe_math")
+        return out.cpu().numpy()
+
+    rng = np.random.default_rng(7)
+    m = 1.0 + rng.random(1 << 20)
+    x = np.concatenate([
+        np.ldexp(m, rng.integers(-1022, 1024, m.size)),                 # every binade
+        np.ldexp(m, rng.integers(-6, 6, m.size)),                       # the stock sizes of the growth models
+        1.0 + (rng.random(1 << 18) - 0.5) * 2.0 ** -6,                  # around 1
+        np.ldexp(1.0 + (np.arange(257) - 0.5).clip(0) / 256.0, 0), np.ldexp(1.0 + (np.arange(257) - 0.5).clip(0) / 256.0, -1),
+        rng.random(1 << 16) * 2.2250738585072014e-308,                  # subnormals
+        [5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1.0, 0.5, 2.0]])
+    with np.errstate(all="ignore"):
+        want = np.log(x)
+        got = probe(0, x)
+        assert _ulps(got, want, 2.0 ** -6).max() < 3.2                  # 2.1 ulp of the truth + numpy's own error
+        # around 1 it is the absolute error that counts (see csrc/normal.cuh); numpy's own error is of the same size there, so
+        # the truth comes from mpmath
+        import mpmath
+
+        near = np.flatnonzero(np.abs(want) < 2.0 ** -6)[::61]
+        mpmath.mp.dps = 40
+        err = [abs(float(mpmath.mpf(float(got[i])) - mpmath.log(mpmath.mpf(float(x[i]))))) for i in near]
+        assert len(err) > 2000 and max(err) < 2.5e-18
+        assert probe(0, np.array([1.0]))[0] == 0.0 and not np.signbit(probe(0, np.array([1.0]))[0])
+        special = np.array([0.0, -0.0, np.inf, -np.inf, -1.0, np.nan, -5e-324])
+        assert np.array_equal(probe(0, special), np.log(special), equal_nan=True)
+        # exp: the range of mu of the growth models, the whole finite range, and the special values
+        y = np.concatenate([(rng.random(1 << 20) - 0.5) * 40.0, (rng.random(1 << 18) - 0.5) * 1500.0, (rng.random(1 << 16) - 0.5) * 2e-3,
+                            [0.0, -0.0, 709.78, 709.79, -745.13, -745.14, -708.4, 700.0, -700.0]])
+        want = np.exp(y)
+        got = probe(1, y)
+        normal = (want > 2.3e-308) & np.isfinite(want)
+        assert np.array_equal(np.isinf(got), np.isinf(want))            # overflow at the same arguments
+        assert _ulps(got[normal], want[normal]).max() < 2.1              # 1.02 ulp of the truth + numpy's own error
+        tiny = want <= 2.3e-308                                          # subnormal or zero results
+        assert tiny.sum() > 100 and np.abs(got[tiny] - want[tiny]).max() <= 2 * 5e-324
+        special = np.array([np.inf, -np.inf, np.nan, 1e308, -1e308])
+        assert np.array_equal(probe(1, special), np.exp(special), equal_nan=True)
