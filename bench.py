@@ -509,14 +509,24 @@ def run_gpu(args):
                 mhz = ck.summary()["sm_mhz"] or 1965
                 pair_steps_per_smsp = (n / 2 / 32) * T / (sm_count * 4)
                 cyc = mhz * 1e6 * fms * 1e-3 / pair_steps_per_smsp
-                port = 2.03 * 2 * (fp64 + alu)             # cycles per pair-step the FP64 + ALU port needs (2.03 cycles each)
+                wide = mix["pipes"].get("imad.wide", 0) / steps                    # per pair-step
+                t_fp64 = 2.03 * 2 * fp64 + 3.9 * wide      # cycles per pair-step the FP64 pipe is taken (see `why`)
+                t_alu = 2.04 * 2 * alu                     # cycles per pair-step on the ALU pipe, which can run beside it
+                port = max(t_fp64, t_alu)
                 fused[name]["roofline"] = {
-                    "kernel": mangled, "bound": "issue port shared by the FP64 and ALU pipes",
-                    "why": "tools/issue_probe.cu on B200: DFMA alone 2.03 cycles, LOP3 alone 2.03, DFMA+LOP3 3.9 -- FP64 and ALU instructions "
-                           "never overlap, IMAD / IMAD.WIDE (Philox) do; so the loop needs 2.03 x (FP64 + ALU instructions) cycles",
+                    "kernel": mangled, "bound": "FP64 pipe time: FP64 instructions + the Philox wide multiplies that do not overlap them",
+                    "why": "tools/issue_probe.cu on B200 (profiles/issue_probe_r02.txt), cycles per warp instruction and sub-partition: DFMA / "
+                           "DADD / DMUL 2.03, LOP3 2.04, IMAD.WIDE 5.1; 2 DFMA + LOP3 4.05 and DFMA + 2 LOP3 4.13 (the lighter pipe hides), "
+                           "DFMA + LOP3 2.59; but DFMA + IMAD.WIDE 6.10 and 8 DFMA + 2 IMAD.WIDE 24.0 = 8 x 2.03 + 2 x 3.9: a wide multiply "
+                           "costs 3.9 cycles ON TOP of the FP64 work.  peak = the time max(2.03 FP64 + 3.9 IMAD.WIDE, 2.04 ALU) would take",
                     "instr_per_pair_step": mix["n"] / steps, "fp64_instr_per_env_step": fp64, "alu_instr_per_env_step": alu,
-                    "port_cycles_per_pair_step": port, "measured_cycles_per_pair_step": cyc, "sm_mhz": mhz,
+                    "imad_wide_per_pair_step": wide, "fp64_pipe_cycles_per_pair_step": t_fp64, "alu_pipe_cycles_per_pair_step": t_alu,
+                    "measured_cycles_per_pair_step": cyc, "sm_mhz": mhz,
                     "achieved": per_gpu, "peak": per_gpu * cyc / port, "unit": UNIT, "frac": port / cyc,
+                    "mix_probe": {"cycles_per_fp64_instr": 3.41, "frac": 3.41 * 2 * fp64 / cyc,
+                                  "what": "a dependency-free loop of 8 DFMA + 8 LOP3 + 2 IMAD.WIDE (the logistic kernel's ratio of FP64 : "
+                                          "ALU : wide multiplies, tools/issue_probe.cu) needs 27.3 cycles = 3.41 per FP64 instruction, i.e. "
+                                          "0.88 of its own pipe-time bound; frac = that loop's time for this kernel's FP64 count / measured"},
                     "fp64_pipe": {"peak": peak_thread_ops, "unit": "fp64 thread-instr/s", "peak_source": "fishing_probe_fp64 (DFMA loop, this run)",
                                   "pipe_frac": fp64 * per_gpu / peak_thread_ops, "alg_fp64_ops_per_env_step": alg_ops,
                                   "useful_frac": alg_ops * per_gpu / peak_thread_ops,

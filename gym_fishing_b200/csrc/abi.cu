@@ -38,6 +38,12 @@ static bool kind_ok(int kind) {
 }
 static bool is_lognormal(int kind) { return kind >= FISHING_V5 && kind <= FISHING_V11; }
 
+#ifdef FISHING_AB_LIBLOG
+constexpr bool kDeriveOnDevice = true;    // timing build with the library's log: host and device logs differ in the last bit
+#else
+constexpr bool kDeriveOnDevice = false;
+#endif
+
 static int growth_fn_of_kind(int kind) {
   switch (kind) {
     case FISHING_V5: return FISHING_FN_ALLEN;
@@ -320,8 +326,11 @@ static int step_impl(const fishing_params* p, int64_t n, int64_t env_id0, uint64
   if (p->kind == FISHING_V10) {                                 // r <- r + alpha BEFORE the draw (growth_models.py:148)
     volatile double r_next = p->r + p->alpha;
     a.gp.r = r_next;
+    if (!kDeriveOnDevice) growth_derive(a.gp, FISHING_FN_BEVERTON_HOLT);   // log(r + 1), K / r for the drifted r
   }
-  a.derive_on_device = p->kind == FISHING_V10;   // so that K1 and the fused K2 (which drifts r in-kernel) agree bit for bit
+  // K1 and the fused K2 (which drifts r in-kernel) must agree bit for bit: growth_derive() gives the same bits on the host and
+  // on the device (csrc/dynamics.cuh), so the host derives once per launch; with the library log they both derive on the device
+  a.derive_on_device = kDeriveOnDevice && p->kind == FISHING_V10;
   // 16-byte vector path: every array that is accessed two-wide must be aligned to its pair size
   bool vec = (n % 2 == 0) && (env_id0 % 2 == 0) && aligned(action, 2 * asz) && aligned(soa.state, 16) &&
              aligned(soa.years, 8) && aligned(out_obs, 16) && aligned(out_reward, 16) && aligned(out_done, 2) &&
@@ -488,11 +497,12 @@ int fishing_population_draw_ln(const fishing_params* p, int32_t model_index, int
       g = t.p[model_index];
     }
   }
-  if (p->kind == FISHING_V10) {     // r <- r + alpha before the draw; the derived fields follow on the device (as in K1 / K2)
+  if (p->kind == FISHING_V10) {     // r <- r + alpha before the draw; the derived fields follow (as in K1 / K2)
     volatile double r_next = p->r + p->alpha;
     g.r = r_next;
+    if (!kDeriveOnDevice) growth_derive(g, fn);
   }
-  return (int)launch_growth_ln(fn, n, x, g, p->kind == FISHING_V10, z, out, static_cast<cudaStream_t>(stream));
+  return (int)launch_growth_ln(fn, n, x, g, kDeriveOnDevice && p->kind == FISHING_V10, z, out, static_cast<cudaStream_t>(stream));
 }
 
 int fishing_bmsy(int32_t kind, double r, double K, double C, int32_t K_is_f64, double* S_out, double* msy_out) {

@@ -24,15 +24,27 @@ struct GrowthP {
   double bq;    // May: b^q
 };
 
-// the derived fields, same operations as the reference's expressions (growth_models.py:213-215,222-225,239,248-253)
+// The derived fields, same operations as the reference's expressions (growth_models.py:213-215,222-225,239,248-253).  The
+// logarithm is csrc/normal.cuh's log_tab on BOTH sides: explicit fma / mul / add on the same tables, so the host (once per
+// launch: K1, also for fishing-v10 whose r drifts from launch to launch) and a kernel (fishing-v10 inside the fused K2, every
+// step) get the same bits.  -DFISHING_AB_LIBLOG: the library's log (then fishing-v10 derives on the device in K1 as well).
+__host__ __device__ inline double growth_log(double x) {
+#if defined(FISHING_AB_LIBLOG)
+  return log(x);
+#elif defined(__CUDA_ARCH__)
+  return log_tab(x, GlobalTabs());
+#else
+  return log_tab(x, HostTabs());
+#endif
+}
 __host__ __device__ inline void growth_derive(GrowthP& g, int fn) {
   g.logA = 0.0; g.B = 0.0; g.omC = 1.0 - g.C; g.bq = 0.0;
   if (fn == FISHING_FN_BEVERTON_HOLT) {
     const double rc = (g.r < 0.0) ? 0.0 : g.r;
-    g.logA = log(rc + 1.0);
+    g.logA = growth_log(rc + 1.0);
     g.B = ((g.K < 0.0) ? 0.0 : g.K) / rc;
   } else if (fn == FISHING_FN_MYERS) {
-    g.logA = log(g.r + 1.0);
+    g.logA = growth_log(g.r + 1.0);
   } else if (fn == FISHING_FN_MAY) {
     g.bq = pow(g.b, g.q);
   }

@@ -28,11 +28,13 @@
 
 #include "normal_tables.cuh"
 
-#if defined(__CUDACC__)
-#define FN_HD __device__ __forceinline__
-#else
 #include <cmath>
 #include <cstring>
+#if defined(__CUDACC__)
+// host + device: the host side of the library derives loop-invariant logarithms (fishing-v6 / v10: log(r + 1)) with the very
+// function the kernels use, so that a value derived on the host and one derived in a kernel agree bit for bit
+#define FN_HD __host__ __device__ __forceinline__
+#else
 using std::exp;
 using std::fabs;
 #define FN_HD inline
@@ -140,7 +142,6 @@ static __constant__ double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHI
                                        FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0,
                                        FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
                                        FISHING_PE2, FISHING_PE1, FISHING_PE0};
-#define FN_COEF(k) FN_C[k]
 // The high word of 1.0 as a literal.  (Reading it from the constant bank turns (w & 0xFFFFF) | 0x3FF00000 into ONE LOP3 instead
 // of two -- tried in round 2, FISHING_AB_ONE_FROM_CONSTANT: one LOP3 less per pair-step, but 2 % slower fused kernels and a 15 %
 // slower trace kernel, the register allocation changes for the worse.)
@@ -189,21 +190,27 @@ __device__ __forceinline__ SharedTabs stage_normal_tables(double2* buf) {
   t.et = reinterpret_cast<const char*>(buf + FISHING_NLOG + 1 + FISHING_NTRIG + 1);
   return t;
 }
-#else
+#endif
+// host copies (the accuracy harness tools/normal_accuracy.cpp, and the host side of the library)
 static const double2 h_normal_log_table[FISHING_NLOG + 1] = FISHING_LOG_TABLE_INIT;
 static const double2 h_normal_trig_table[FISHING_NTRIG + 1] = FISHING_TRIG_TABLE_INIT;
 static const double h_exp_table[64] = FISHING_EXP_TABLE_INIT;
-static const double FN_C[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
-                                FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0,
-                                FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
-                                FISHING_PE2, FISHING_PE1, FISHING_PE0};
-#define FN_COEF(k) FN_C[k]
-#define FN_ONE_HI 0x3FF00000u
+static const double FN_C_H[18] = {FISHING_Q3, FISHING_Q2, FISHING_Q1, FISHING_Q0, FISHING_M2LN2, FISHING_PS2,
+                                  FISHING_PS1, FISHING_PS0, FISHING_PC2, FISHING_PC1, FISHING_PC0,
+                                  FISHING_EXP_64_LN2, FISHING_EXP_NLN2_64_HI, FISHING_EXP_NLN2_64_LO, FISHING_PE3,
+                                  FISHING_PE2, FISHING_PE1, FISHING_PE0};
 struct HostTabs {
   double exp_at(uint32_t byte_off) const { return h_exp_table[byte_off >> 3]; }
   double2 log_at(uint32_t byte_off) const { return h_normal_log_table[byte_off >> 4]; }
   double2 trig_at(uint32_t byte_off) const { return h_normal_trig_table[byte_off >> 4]; }
 };
+#if defined(__CUDA_ARCH__)
+#define FN_COEF(k) FN_C[k]
+#else
+#define FN_COEF(k) FN_C_H[k]
+#endif
+#if !defined(__CUDACC__)
+#define FN_ONE_HI 0x3FF00000u
 #endif
 
 template <class Tabs>

@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 //     `done` is kept aside, which costs one select less than gating the addition.
 // Results are bit-identical to the generic kernel (tests/test_gpu_parity.py runs both against the oracle).
 // A/B (tools/ab_build.py imad_select): float64 selects of the fast path done as b + m (a - b) on the integer halves, m = 0 / 1
-// -- IADD / IMAD instead of two FSEL, which share the issue port of the FP64 pipe.
+// -- IADD / IMAD instead of two FSEL.  Measured 6 - 23 % slower (profiles/ab_r02.md): more instructions, and the ALU pipe was
+// not the limit.
 #ifdef FISHING_AB_IMAD_SELECT
 __device__ __forceinline__ double sel64(bool p, double a, double b) {   // p ? a : b
   const unsigned m = p ? 1u : 0u;

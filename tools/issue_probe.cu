@@ -24,6 +24,7 @@ constexpr int ITER = 4096;
 #define IMADW_() asm volatile("{.reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t;}" : "+r"(u[c]), "+r"(v[c]) : "r"(k))
 #define IMADHI_() asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(v[c]) : "r"(k))
 #define FSEL_() asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.f32 %0, %0, %2, p;}" : "+f"(f[c]) : "r"(u[c]), "f"(g))
+#define SHF_() asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(u[c]) : "r"(v[c]))
 #define FFMA_() asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(g), "f"(g))
 
 struct Mode { const char* name; int n_instr; };
@@ -32,6 +33,12 @@ static const Mode MODES[] = {
     {"DFMA+LOP3", 2}, {"DFMA+2LOP3", 3}, {"DFMA+3 (2LOP3+IADD)", 4}, {"DFMA+IMAD", 2}, {"DFMA+IMAD.WIDE", 2}, {"DFMA+FFMA", 2},
     {"LOP3+IMAD.WIDE", 2}, {"2LOP3+IMAD.WIDE", 3}, {"LOP3+IMAD", 2}, {"LOP3+FFMA", 2}, {"DSETP+SEL", 2}, {"DFMA+DSETP+SEL", 3},
     {"2DFMA+2LOP3+IADD+IMAD.WIDE (K2-like)", 6}, {"LOP3+IADD (both ALU)", 2}, {"DFMA+DADD", 2},
+    // does the ORDER of FP64 and ALU instructions inside a warp matter?  (same counts, alternating against grouped)
+    {"DFMA+LOP3 ordered D D L L", 2}, {"DFMA+LOP3 ordered 4D 4L", 2}, {"DFMA+LOP3 ordered 8D 8L", 2}, {"D D L", 3}, {"D D D L", 4},
+    {"D L L L", 4}, {"ISETP+FSEL", 2}, {"DFMA+ISETP+FSEL", 3}, {"2DFMA+ISETP+FSEL", 4}, {"DFMA+SHF", 2},
+    // the instruction mix of the fused kernel's loop, scaled to 8 FP64 (per pair-step it is 64 FP64, 60 ALU, 16 IMAD.WIDE, 13 IMAD,
+    // 13 IADD), without its dependencies: per group of 8 chains
+    {"mix 8D+2W (per D)", 1}, {"mix 8D+8L+2W (per D)", 1}, {"mix 8D+8L+2W+2IMAD+2IADD (per D; K2's mix)", 1}, {"mix 8D+4L+2W (per D)", 1},
 };
 constexpr int NMODES = sizeof(MODES) / sizeof(MODES[0]);
 
@@ -42,13 +49,13 @@ __global__ void __launch_bounds__(1024) probe(double* out, uint32_t* outi, long 
   float f[CH];
   const float g = (float)b;
 #pragma unroll
-  for (int c = 0; c < CH; ++c) { x[c] = a + c + threadIdx.x; u[c] = k + c * 77u + threadIdx.x; v[c] = k * 3u + c; f[c] = (float)c; }
+  for (int c = 0; c < CH; ++c) { x[c] = a + c + threadIdx.x; u[c] = k + c * 77u + threadIdx.x; v[c] = k * 3u + c + threadIdx.x * 5u; f[c] = (float)c; }   // v per thread: a uniform v would be re-materialised with a MOV per use
   __syncthreads();
   const long long c0 = clock64();
 #pragma unroll 1
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
+    for (int c = 0; c < CH && !(MODE >= 24 && MODE <= 26); ++c) {
       if (MODE == 0) DFMA_();
       if (MODE == 1) DADD_();
       if (MODE == 2) DMUL_();
@@ -73,6 +80,37 @@ __global__ void __launch_bounds__(1024) probe(double* out, uint32_t* outi, long 
       if (MODE == 21) { DFMA_(); LOP3U_(); DADD_(); IADD_(); IMADW_(); LOP3V_(); }
       if (MODE == 22) { LOP3U_(); IADD_(); }
       if (MODE == 23) { DFMA_(); DADD_(); }
+      if (MODE == 27) { DFMA_(); DADD_(); LOP3U_(); }
+      if (MODE == 28) { DFMA_(); DADD_(); DMUL_(); LOP3U_(); }
+      if (MODE == 29) { DFMA_(); LOP3U_(); LOP3V_(); LOP3U_(); }
+      if (MODE == 30) FSEL_();
+      if (MODE == 31) { DFMA_(); FSEL_(); }
+      if (MODE == 32) { DFMA_(); DADD_(); FSEL_(); }
+      if (MODE == 33) { DFMA_(); SHF_(); }
+      if (MODE == 34) { DFMA_(); if ((c & 3) == 0) IMADW_(); }
+      if (MODE == 35) { DFMA_(); LOP3U_(); if ((c & 3) == 0) IMADW_(); }
+      if (MODE == 36) { DFMA_(); LOP3U_(); if ((c & 3) == 0) IMADW_(); if ((c & 3) == 1) IMAD_(); if ((c & 3) == 2) IADD_(); }
+      if (MODE == 37) { DFMA_(); if (c & 1) LOP3U_(); if ((c & 3) == 0) IMADW_(); }
+    }
+    // the same 8 DFMA + 8 LOP3 per iteration as "DFMA+LOP3", in a different ORDER inside the warp (normalised per D + L pair)
+    if (MODE == 24) {
+#pragma unroll
+      for (int c = 0; c < CH; c += 2) { DFMA_(); c++; DFMA_(); c--; LOP3U_(); c++; LOP3U_(); c--; }
+    }
+    if (MODE == 25) {
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 4) {
+#pragma unroll
+        for (int c = c0; c < c0 + 4; ++c) DFMA_();
+#pragma unroll
+        for (int c = c0; c < c0 + 4; ++c) LOP3U_();
+      }
+    }
+    if (MODE == 26) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) DFMA_();
+#pragma unroll
+      for (int c = 0; c < CH; ++c) LOP3U_();
     }
   }
   const long long c1 = clock64();

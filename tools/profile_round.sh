@@ -18,6 +18,11 @@ $NCU --set full -k regex:step_kernel_vec2 --launch-skip 40 --launch-count 3 -o $
 python tools/k2_bench.py > $OUT/plain_k2_$TAG.json 2> $OUT/plain_k2_$TAG.err || { echo "plain k2 failed"; exit 1; }
 K2B_T=200 $NCU --set full -k regex:rollout_fast_kernel --launch-skip 2 --launch-count 2 -o $OUT/k2_$TAG -f python tools/k2_bench.py > $OUT/ncu_k2_$TAG.log 2>&1
 K2B_T=200 $NCU --set full -k regex:rollout_sweep --launch-skip 2 --launch-count 1 -o $OUT/k2sweep_$TAG -f python tools/k2_bench.py > $OUT/ncu_k2s_$TAG.log 2>&1
+# next row f1: the K1 kernel of fishing-v8 (Myers: two logs, a power and an exp per step, all table-assisted) at 2^20 envs
+if [ "${PROFILE_F1:-1}" != 0 ]; then
+  python benchmarks/run_configs.py --only f1 > $OUT/plain_f1_$TAG.jsonl 2> $OUT/plain_f1_$TAG.err || { echo "plain f1 failed"; exit 1; }
+  $NCU --set full --kernel-name-base demangled -k "regex:step_kernel_vec2<\\(int\\)4," --launch-skip 60 --launch-count 1 -o $OUT/k1v8_$TAG -f python benchmarks/run_configs.py --only f1 > $OUT/ncu_k1v8_$TAG.log 2>&1
+fi
 summarise() {   # the tables are made on the box: only text has to travel back (gpurun merges at most 64 MiB)
   python tools/launch_table.py $OUT/launches_$TAG.csv > $OUT/launch_table_$TAG.md 2>&1
   python tools/ncu_summary.py $OUT/*_$TAG.ncu-rep > $OUT/ncu_tables_$TAG.md 2>&1
