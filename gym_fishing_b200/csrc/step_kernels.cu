@@ -88,12 +88,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // terminal-observation outputs): their null tests and address arithmetic -- about 20 of the kernel's 333 instructions per
 // pair, in a kernel that is bound by instruction issue -- are compiled out (cfg 2: 6.83 -> 6.53 us per launch).  The
 // rollout-buffer loop of bench.py and FishingVecEnv's torch path run this instantiation.  The lean fishing-v4 kernel is
-// held to 48 registers (5 resident blocks per SM instead of 4; 36 bytes of spill): 6.78 -> 6.57 ms per 128 steps of cfg 4.
+// held to 48 registers (1280 resident threads per SM instead of 1024): 6.78 -> 6.57 ms per 128 steps of cfg 4.
 // EXTRA (never together with LEAN) = the instantiation that also keeps the VecMonitor statistics and writes float32 copies of
 // observations / rewards (fishing_step_ex): a kernel of its own, so that neither the lean nor the plain instantiation pays
 // registers for it.
 template <int GROWTH, int PM, int ACT, int BS = 128, bool LEAN = false, bool EXTRA = false>
-__global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 : 0) step_kernel_vec2(const StepArgs a) {
+__global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS <= 256) ? 1280 / BS : 0) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
   // fishing-v4 reset jobs of the whole block (see the end of the kernel)
@@ -247,6 +247,22 @@ __global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS == 256) ? 5 
       __threadfence_block();
       const int total = (int)*reinterpret_cast<volatile unsigned*>(&s_count);
       const int64_t block0 = 2 * (int64_t)(blockIdx.x * (unsigned)BS);
+#ifdef FISHING_AB_V4_ILP2      // timing build: two jobs per lane and pass (two independent Philox + Box-Muller chains)
+      for (int k = lane; k < total; k += 64) {
+        const bool two = k + 32 < total;
+        const int64_t ia = block0 + reinterpret_cast<volatile uint16_t*>(s_job)[k];
+        const int64_t ib = two ? block0 + reinterpret_cast<volatile uint16_t*>(s_job)[k + 32] : ia;
+        const Normal2 da = normal_pair_keys(a.keys, (uint64_t)(a.env_id0 + ia), a.step_idx, FISHING_STREAM_AUTORESET);
+        const Normal2 db = normal_pair_keys(a.keys, (uint64_t)(a.env_id0 + ib), a.step_idx, FISHING_STREAM_AUTORESET);
+        a.K_env[ia] = v4_param(a.K_mean, a.sigma_p, da.z0);
+        a.r_env[ia] = v4_param(a.r_mean, a.sigma_p, da.z1);
+        if (two) {
+          a.K_env[ib] = v4_param(a.K_mean, a.sigma_p, db.z0);
+          a.r_env[ib] = v4_param(a.r_mean, a.sigma_p, db.z1);
+        }
+      }
+      if (false)
+#endif
       for (int k = lane; k < total; k += 32) {
         const int64_t i = block0 + reinterpret_cast<volatile uint16_t*>(s_job)[k];
 #ifdef FISHING_AB_V4_NODRAW      // timing build: what do the draws cost (the scattered writes stay)
@@ -499,11 +515,19 @@ static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm) {
 #ifndef FISHING_K1_BS
 #define FISHING_K1_BS 256      // threads per block of the lock-step kernel (timing builds: 128 / 512)
 #endif
-constexpr int K1_BS = FISHING_K1_BS;
+constexpr int K1_BS_DEFAULT = FISHING_K1_BS;
+#ifndef FISHING_K1_BS_V4
+// per-environment parameters (fishing-v4): 128-thread blocks.  The warp that signs off last redraws (K, r) for the block's resets
+// while the block's registers stay allocated; with ~10 % of the environments resetting per step a 256-thread block needs two 32-job
+// passes, a 128-thread block one (cfg 4, random actions: 8.41e10 -> 8.63e10 env-steps/s; 64 threads: 8.74e10 but -4 % at ~1 %
+// resets; two jobs per lane and pass instead: no gain -- profiles/ab_r02.md)
+#define FISHING_K1_BS_V4 128
+#endif
 
 template <int GROWTH, int PM, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, bool vec, cudaStream_t st) {
   constexpr bool CAN_LEAN = true;
+  constexpr int K1_BS = PM == P_PERENV ? FISHING_K1_BS_V4 : K1_BS_DEFAULT;
   const bool extra = a.ep_return || a.out_obs32 || a.out_reward32 || a.out_done_bits;
   const bool lean = CAN_LEAN && !extra && !a.noise && !a.reset_noise && !a.out_obs2 && !a.out_stock && !a.out_harvest && !a.out_terminal;
   if (vec) {
