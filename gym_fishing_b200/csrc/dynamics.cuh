@@ -139,6 +139,28 @@ __device__ __forceinline__ double div_k(double a, double K, const KDiv& kd) {
   }
   return div_z(a, K);
 }
+// fishing-v4: the divisor is the environment's OWN K, and a step divides by it twice (x1 / K in population_draw, x2 / K in
+// get_state).  One correctly rounded reciprocal -- __drcp_rn(K), the same bits as the host's 1.0 / K -- serves both quotients
+// through div_k (5 FP64 instructions each) instead of two hardware division sequences (~25 instructions each with the
+// zero-numerator patch of div_z): the fishing-v4 lock-step kernel executed 389 instructions per warp outside its redraw pass,
+// about 100 of them in these four divisions of a pair.  -DFISHING_V4_RCP=0: the round-1 form (A/B, profiles/ab_r02.md).
+#ifndef FISHING_V4_RCP
+#define FISHING_V4_RCP 1
+#endif
+__device__ __forceinline__ KDiv kdiv_env(double K, int odd = 0) {
+  KDiv k;
+  k.fast = (K >= 0x1p-500 && K <= 0x1p500) ? 1 : 0;   // positive ordinary numbers only (false for NaN, 0 and the clipped 1e6 is fine)
+  k.rK = __drcp_rn(K);                                 // never read when !fast
+  k.odd = odd;
+  return k;
+}
+// x / K by parameter mode; for P_PERENV `kd` has to be the ENVIRONMENT's (kdiv_env), never the launch's
+template <int PM>
+__device__ __forceinline__ double div_pm(double x, double K, const KDiv& kd) {
+  if (PM == P_KONE) return x;
+  if (PM == P_UNIFORM || FISHING_V4_RCP) return div_k(x, K, kd);
+  return div_z(x, K);
+}
 
 // (a / n_actions) * K for a Discrete action, base_fishing_env.py:139-141
 template <int PM>
@@ -163,7 +185,7 @@ __device__ __forceinline__ double action_discrete(double q, double n_actions, do
 template <int GROWTH, int PM, class Tabs = GlobalTabs>
 __device__ __forceinline__ double grow(double x1, double r, double K, double C, double sigma, double z, bool noisy,
                                        const KDiv& kd = KDiv(), const Tabs& tb = Tabs()) {
-  const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, K, kd) : div_z(x1, K));
+  const double frac = div_pm<PM>(x1, K, kd);      // P_PERENV: kd is the environment's own (step_core)
   const double room = __dsub_rn(1.0, frac);
   if (GROWTH == LOGISTIC) {
     double t = __dadd_rn(x1, __dmul_rn(__dmul_rn(r, x1), room));
@@ -304,12 +326,13 @@ __device__ __forceinline__ StepOut step_core(double s, double quota, double z, d
   // positive number or NaN for every input, and Python's max(v, 0.0) returns v in all three cases
   const double x1 = __dsub_rn(x, h);
   double x2;
-  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy, kd);
+  // fishing-v4: one reciprocal of this environment's K for the step's two quotients (kdiv_env)
+  const KDiv kde = (PM == P_PERENV && FISHING_V4_RCP && (GROWTH == LOGISTIC || GROWTH == TIPPING)) ? kdiv_env(K, kd.odd) : kd;
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) x2 = grow<GROWTH, PM>(x1, r, K, C, sigma, z, noisy, kde);
   else x2 = grow_ln<GROWTH>(x1, *gp, *tab, model, z, noisy);
   StepOut o;
   // get_state :162-164 (the log-normal family always takes the general-K path, with K = 1 by default: div_u)
-  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING)
-    o.s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, K, kd) : div_z(x2, K)), 1.0);
+  if constexpr (GROWTH == LOGISTIC || GROWTH == TIPPING) o.s2 = __dsub_rn(div_pm<PM>(x2, K, kde), 1.0);
   else o.s2 = __dsub_rn(div_u(x2, K), 1.0);
   o.reward = py_max(h, 0.0);                        // :74
   o.dead = x2 <= 0.0;                               // :78

@@ -348,6 +348,7 @@ struct FastEnv {
   double s, K, r, S, ret, ret_snap, quota_const;
   int years, done_step;
   bool frozen;
+  KDiv kdv;   // fishing-v4: the reciprocal of this environment's K (dynamics.cuh: kdiv_env), renewed when K is redrawn
 };
 
 // see "reward" above: does this environment enter with a negative stock?  (Then its first step runs with the comparison.)
@@ -359,6 +360,7 @@ __device__ __forceinline__ bool fast_env_enter(FastEnv& e) {
   e.done_step = -1;
   e.frozen = false;
   e.quota_const = 0.0;
+  if (PM == P_PERENV && FISHING_V4_RCP) e.kdv = kdiv_env(e.K);
   return x < 0.0;
 }
 
@@ -388,7 +390,8 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
   const double h = sel64(quota < x, quota, x);                   // min(x, quota), harvest_draw
   const double x1 = __dsub_rn(x, h);                             // == max(x - h, 0.0)
-  const double frac = PM == P_KONE ? x1 : (PM == P_UNIFORM ? div_k(x1, e.K, a.kd) : div_z(x1, e.K));
+  const KDiv& kdq = (PM == P_PERENV && FISHING_V4_RCP) ? e.kdv : a.kd;      // whose reciprocal the step's two quotients use
+  const double frac = div_pm<PM>(x1, e.K, kdq);
   const double room = __dsub_rn(1.0, frac);
   double g;
   if (GROWTH == LOGISTIC) {
@@ -403,7 +406,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
   const double x2 = sel64(alive, g, 0.0);
-  const double s2 = __dsub_rn(PM == P_KONE ? x2 : (PM == P_UNIFORM ? div_k(x2, e.K, a.kd) : div_z(x2, e.K)), 1.0);
+  const double s2 = __dsub_rn(div_pm<PM>(x2, e.K, kdq), 1.0);
   const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;
@@ -422,6 +425,7 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
         const Normal2 d = normal_pair(a.seed, gid, a.step0 + (uint64_t)t, FISHING_STREAM_AUTORESET);
         e.K = v4_param(a.K_mean, a.sigma_p, d.z0);
         e.r = v4_param(a.r_mean, a.sigma_p, d.z1);
+        if (FISHING_V4_RCP) e.kdv = kdiv_env(e.K);
         if (POLICY == FISHING_POLICY_MSY) {
           double unused;
           e.quota_const = policy_quota_msy<PM>(a, e.K, unused);

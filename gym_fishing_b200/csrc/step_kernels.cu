@@ -92,8 +92,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // EXTRA (never together with LEAN) = the instantiation that also keeps the VecMonitor statistics and writes float32 copies of
 // observations / rewards (fishing_step_ex): a kernel of its own, so that neither the lean nor the plain instantiation pays
 // registers for it.
+#ifndef FISHING_V4_RESIDENT
+#define FISHING_V4_RESIDENT 1280      // resident threads per SM the lean fishing-v4 kernel is compiled for (timing build: 1536 = 40 registers)
+#endif
 template <int GROWTH, int PM, int ACT, int BS = 128, bool LEAN = false, bool EXTRA = false>
-__global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS <= 256) ? 1280 / BS : 0) step_kernel_vec2(const StepArgs a) {
+__global__ void __launch_bounds__(BS, (LEAN && PM == P_PERENV && BS <= 256) ? FISHING_V4_RESIDENT / BS : 0) step_kernel_vec2(const StepArgs a) {
   using AT2 = typename ActT<ACT>::vec2;
   if (a.flags & STEP_FLAG_PDL) pdl_launch_dependents();
   // fishing-v4 reset jobs of the whole block (see the end of the kernel)
@@ -520,7 +523,10 @@ constexpr int K1_BS_DEFAULT = FISHING_K1_BS;
 // per-environment parameters (fishing-v4): 128-thread blocks.  The warp that signs off last redraws (K, r) for the block's resets
 // while the block's registers stay allocated; with ~10 % of the environments resetting per step a 256-thread block needs two 32-job
 // passes, a 128-thread block one (cfg 4, random actions: 8.41e10 -> 8.63e10 env-steps/s; 64 threads: 8.74e10 but -4 % at ~1 %
-// resets; two jobs per lane and pass instead: no gain -- profiles/ab_r02.md)
+// resets; two jobs per lane and pass instead: no gain -- profiles/ab_r02.md).  Also measured and NOT kept (r02o / r02p there): a
+// persistent kernel that walks per-warp tiles with the next tile's loads in flight (in registers, or staged with cp.async in
+// per-lane shared-memory slots) and redraws from a warp-private queue in full 32-lane passes -- bit-identical, but 7.1 - 7.3e10
+// against 8.7e10 env-steps/s, and slower even without resets (1.00e11 against 1.12e11).
 #define FISHING_K1_BS_V4 128
 #endif
 

@@ -844,3 +844,49 @@ def test_v4_vector_path_with_partial_last_warp(n):
         assert np.array_equal(done.cpu().numpy(), exp["done"]) and exp["done"].sum() > n
         assert np.array_equal(obs.cpu().numpy(), exp["obs"]) and np.array_equal(rew.cpu().numpy(), exp["reward"])
         assert np.array_equal(b.K_env.cpu().numpy(), exp["K"]) and np.array_equal(b.r_env.cpu().numpy(), exp["r"])
+
+
+@pytest.mark.parametrize("adt", ["f64", "f32"])
+def test_v4_whole_batch_equals_its_parts_with_noise_and_redraws(adt):
+    """fishing-v4, 393 282 environments (a partial last warp) over several episodes each, process noise on, ~a sixth of the
+    quotas taking everything: the whole batch, stepped per launch and through step_many (programmatic dependent launch
+    between the steps, phase-A L2 prefetch on), against the same environment ids stepped as three smaller batches.
+    Observations, rewards, dones, years and the redrawn (K, r) agree bit for bit -- including the episode of an
+    environment whose redrawn K was clipped to 0 (x / 0: NaN observations until its next reset; the oracle does the same).
+    (Written while a persistent variant of the kernel was measured, profiles/ab_r02.md r02o / r02p.)"""
+    torch = _torch()
+    n = (1 << 18) + (1 << 17) + 66
+    T = 14
+    cfg = dict(r=0.3, K=1.0, sigma=0.05, x0=0.75, Tmax=5, sigma_p=0.2, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.rand((T, n), dtype=torch.float64, device="cuda", generator=g) * 1.2 - 1.0     # ~ a sixth of the quotas take everything
+    if adt == "f32":
+        acts = acts.float()
+
+    def run(n_part, lo, many):
+        b = make_batch("v4", n_part, env_id0=lo, auto_reset=True, **cfg)
+        b.reset()
+        obs = torch.empty(T, n_part, dtype=torch.float64, device="cuda")
+        rew = torch.empty_like(obs)
+        done = torch.empty(T, n_part, dtype=torch.uint8, device="cuda")
+        a = acts[:, lo:lo + n_part].contiguous()
+        if many:
+            b.step_many(a, obs, rew, done)
+        else:
+            for t in range(T):
+                b.step(a[t], out_obs=obs[t], out_reward=rew[t], out_done=done[t])
+        torch.cuda.synchronize()
+        return obs, rew, done, b.K_env.clone(), b.r_env.clone(), b.years.clone()
+
+    parts = []
+    for lo, n_part in ((0, 1 << 17), (1 << 17, 1 << 17), (1 << 18, n - (1 << 18))):
+        assert n_part // 2 < (1 << 17)
+        parts.append(run(n_part, lo, many=False))
+    ref = [torch.cat([p[k] for p in parts], dim=-1) for k in range(6)]
+    assert int(ref[2].sum()) > 2 * n                     # every environment went through several resets
+    for many in (False, True):
+        got = run(n, 0, many)
+        for k, what in enumerate(("obs", "reward", "done", "K", "r", "years")):
+            # bit patterns: an environment whose redrawn K was clipped to 0 carries NaN observations for an episode (x / 0)
+            a_, b_ = (got[k].view(torch.int64), ref[k].view(torch.int64)) if got[k].dtype == torch.float64 else (got[k], ref[k])
+            assert torch.equal(a_, b_), (what, many)
