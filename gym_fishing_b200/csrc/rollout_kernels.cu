@@ -25,6 +25,10 @@
 namespace fishing {
 
 constexpr int K2_UNROLL = FISHING_K2_UNROLL;
+#ifndef FISHING_K2_FAST_BS
+#define FISHING_K2_FAST_BS 128    // threads per block of rollout_fast_kernel (timing builds: 64 / 32 with FISHING_K2_MINBLOCKS 9 / 18)
+#endif
+constexpr int K2_FAST_BS = FISHING_K2_FAST_BS;
 #ifndef FISHING_SWEEP_UNROLL
 #define FISHING_SWEEP_UNROLL 4
 #endif
@@ -455,12 +459,12 @@ __device__ __forceinline__ double fast_env_return(const FastEnv& e) {
 // TRACE: per-step observation / reward / done rows [T, n] written with streaming stores (the rollout-buffer fill of a
 // whole chunk in one launch).  Not combined with freeze-on-done or an action trace; those go to the generic kernel.
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
-__global__ void __launch_bounds__(128, FISHING_K2_MINBLOCKS) rollout_fast_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(K2_FAST_BS, FISHING_K2_MINBLOCKS) rollout_fast_kernel(const RolloutArgs a) {
   // the Box-Muller tables, staged once per block for the T draws of every thread (normal.cuh)
   constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
   __shared__ double2 s_tab[TABLES ? NORMAL_TABLE_ENTRIES : 1];
   SharedTabs tb = {};
-  if (TABLES) tb = stage_normal_tables<128>(s_tab);
+  if (TABLES) tb = stage_normal_tables<K2_FAST_BS>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
   Lanes L;
@@ -796,10 +800,11 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
     else launch_sweep_m<GROWTH, PM, false, SWEEP_LV>(a, (int)sgrid, block, st);
   } else if (fast) {
     const bool noisy = a.sigma != 0.0;
+    const int fgrid = (int)((threads + K2_FAST_BS - 1) / K2_FAST_BS);
     switch (policy) {
-      case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, (int)grid, block, st); break;
-      case FISHING_POLICY_ESCAPEMENT: launch_fast_n<GROWTH, PM, FISHING_POLICY_ESCAPEMENT>(a, noisy, (int)grid, block, st); break;
-      default: launch_fast_n<GROWTH, PM, FISHING_POLICY_MSY>(a, noisy, (int)grid, block, st); break;
+      case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, fgrid, K2_FAST_BS, st); break;
+      case FISHING_POLICY_ESCAPEMENT: launch_fast_n<GROWTH, PM, FISHING_POLICY_ESCAPEMENT>(a, noisy, fgrid, K2_FAST_BS, st); break;
+      default: launch_fast_n<GROWTH, PM, FISHING_POLICY_MSY>(a, noisy, fgrid, K2_FAST_BS, st); break;
     }
   } else {
     switch (policy) {
