@@ -29,6 +29,14 @@ constexpr int K2_UNROLL = FISHING_K2_UNROLL;
 #define FISHING_K2_FAST_BS 128    // threads per block of rollout_fast_kernel (timing builds: 64 / 32 with FISHING_K2_MINBLOCKS 9 / 18)
 #endif
 constexpr int K2_FAST_BS = FISHING_K2_FAST_BS;
+// Timing build (-DFISHING_K2_TIPPING_WARPS5=1, profiles/ab_r02.md r02q): the tipping-point instantiations in 64-thread blocks compiled for
+// 9 per SM (92 - 96 registers without a spill, 10 resident blocks = a fifth warp per scheduler).  Plain mode gains 3 % (2.10 -> 2.17e11),
+// the freeze-on-done instantiation that cfg 3 runs loses 1 - 2 % (bench.py: 2.01 -> 1.98e11), the logistic kernel loses 8 %: not the default.
+#ifndef FISHING_K2_TIPPING_WARPS5
+#define FISHING_K2_TIPPING_WARPS5 0
+#endif
+__host__ __device__ constexpr int fast_bs(int growth) { return (FISHING_K2_TIPPING_WARPS5 && growth == TIPPING) ? 64 : K2_FAST_BS; }
+__host__ __device__ constexpr int fast_minblocks(int growth) { return (FISHING_K2_TIPPING_WARPS5 && growth == TIPPING) ? 9 : FISHING_K2_MINBLOCKS; }
 #ifndef FISHING_SWEEP_UNROLL
 #define FISHING_SWEEP_UNROLL 4
 #endif
@@ -459,12 +467,12 @@ __device__ __forceinline__ double fast_env_return(const FastEnv& e) {
 // TRACE: per-step observation / reward / done rows [T, n] written with streaming stores (the rollout-buffer fill of a
 // whole chunk in one launch).  Not combined with freeze-on-done or an action trace; those go to the generic kernel.
 template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
-__global__ void __launch_bounds__(K2_FAST_BS, FISHING_K2_MINBLOCKS) rollout_fast_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(fast_bs(GROWTH), fast_minblocks(GROWTH)) rollout_fast_kernel(const RolloutArgs a) {
   // the Box-Muller tables, staged once per block for the T draws of every thread (normal.cuh)
   constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
   __shared__ double2 s_tab[TABLES ? NORMAL_TABLE_ENTRIES : 1];
   SharedTabs tb = {};
-  if (TABLES) tb = stage_normal_tables<K2_FAST_BS>(s_tab);
+  if (TABLES) tb = stage_normal_tables<fast_bs(GROWTH)>(s_tab);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (a.n >> 1)) return;
   Lanes L;
@@ -800,11 +808,12 @@ static cudaError_t launch_rollout_p(const RolloutArgs& a, int policy, cudaStream
     else launch_sweep_m<GROWTH, PM, false, SWEEP_LV>(a, (int)sgrid, block, st);
   } else if (fast) {
     const bool noisy = a.sigma != 0.0;
-    const int fgrid = (int)((threads + K2_FAST_BS - 1) / K2_FAST_BS);
+    constexpr int FBS = fast_bs(GROWTH);
+    const int fgrid = (int)((threads + FBS - 1) / FBS);
     switch (policy) {
-      case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, fgrid, K2_FAST_BS, st); break;
-      case FISHING_POLICY_ESCAPEMENT: launch_fast_n<GROWTH, PM, FISHING_POLICY_ESCAPEMENT>(a, noisy, fgrid, K2_FAST_BS, st); break;
-      default: launch_fast_n<GROWTH, PM, FISHING_POLICY_MSY>(a, noisy, fgrid, K2_FAST_BS, st); break;
+      case FISHING_POLICY_ACTIONS: launch_fast_n<GROWTH, PM, FISHING_POLICY_ACTIONS>(a, noisy, fgrid, FBS, st); break;
+      case FISHING_POLICY_ESCAPEMENT: launch_fast_n<GROWTH, PM, FISHING_POLICY_ESCAPEMENT>(a, noisy, fgrid, FBS, st); break;
+      default: launch_fast_n<GROWTH, PM, FISHING_POLICY_MSY>(a, noisy, fgrid, FBS, st); break;
     }
   } else {
     switch (policy) {

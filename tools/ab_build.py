@@ -28,6 +28,7 @@ VARIANTS = {
     "v4rcp0": ["-DFISHING_V4_RCP=0"],                      # fishing-v4's two quotients per step as hardware divisions (until r02n)
     "v4res1536": ["-DFISHING_V4_RESIDENT=1536"],           # the lean fishing-v4 K1 compiled for 1536 resident threads (40 registers)
     "k2bs64": ["-DFISHING_K2_FAST_BS=64"], "k2bs64mb9": ["-DFISHING_K2_FAST_BS=64", "-DFISHING_K2_MINBLOCKS=9"],   # fused kernel in 64-thread blocks (8 blocks = today's 16 warps per SM; 9 = 18 warps at 112 registers)
+    "k2tip5": ["-DFISHING_K2_TIPPING_WARPS5=1"],           # only the tipping-point instantiations at 64 threads x 9 blocks
     "k2bs32mb18": ["-DFISHING_K2_FAST_BS=32", "-DFISHING_K2_MINBLOCKS=18"], "k2bs32mb17": ["-DFISHING_K2_FAST_BS=32", "-DFISHING_K2_MINBLOCKS=17"],
     "liblog": ["-DFISHING_AB_LIBLOG"],                     # fishing-v5..v11 with libdevice's log / pow instead of csrc/normal.cuh:log_tab
     "imad_select": ["-DFISHING_AB_IMAD_SELECT"],
