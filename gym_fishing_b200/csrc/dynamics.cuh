@@ -149,7 +149,7 @@ __device__ __forceinline__ double div_k(double a, double K, const KDiv& kd) {
 #endif
 __device__ __forceinline__ KDiv kdiv_env(double K, int odd = 0) {
   KDiv k;
-  k.fast = (K >= 0x1p-500 && K <= 0x1p500) ? 1 : 0;   // positive ordinary numbers only (false for NaN, 0 and the clipped 1e6 is fine)
+  k.fast = (K >= 0x1p-500 && K <= 0x1p500) ? 1 : 0;   // positive ordinary numbers only: false for NaN and for a K clipped to 0 (then div_z)
   k.rK = __drcp_rn(K);                                 // never read when !fast
   k.odd = odd;
   return k;
