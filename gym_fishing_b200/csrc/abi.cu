@@ -426,6 +426,13 @@ int fishing_rollout(const fishing_params* p, int64_t n, int64_t env_id0, const f
   a.keys = philox_round_keys(p->seed);
   a.r = p->r; a.K = p->K; a.sigma = p->sigma; a.C = p->C;
   a.s_reset = reset_state_value(p);
+  {
+    volatile double xr = a.s_reset + 1.0;        // volatile: one binary64 rounding each, whatever the host compiler would like to fold
+    volatile double back = xr - 1.0;
+    a.x_reset_fold = xr;
+    const double b = back, s0 = a.s_reset;
+    a.fold_reset = (std::memcmp(&b, &s0, sizeof(double)) == 0 && xr >= 0.0) ? 1 : 0;    // same BITS (a signed zero counts)
+  }
   a.K_mean = p->K; a.r_mean = p->r; a.sigma_p = p->sigma_p;
   a.n_actions = (double)p->n_actions;
   a.rcp_n_actions = 1.0 / (double)p->n_actions;

@@ -91,6 +91,11 @@ struct RolloutArgs {
   const void* __restrict__ actions;
   const double* __restrict__ noise;
   int64_t noise_id_div;
+  // auto-reset in the fused fast path with K = 1: the reset is folded into the np.maximum select -- the stock becomes x_reset_fold
+  // = s_reset + 1 in the step that ends an episode, and s = x - 1 then IS s_reset -- when the host has checked that
+  // (s_reset + 1) - 1 == s_reset in binary64 (fold_reset; otherwise the state is overwritten after the step as before)
+  double x_reset_fold;
+  int32_t fold_reset;
   double* state;
   int32_t* years;
   double* K_env;

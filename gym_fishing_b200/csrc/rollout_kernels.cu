@@ -381,10 +381,14 @@ __device__ __forceinline__ bool fast_env_enter(FastEnv& e) {
 // parameter, so that the plain loop carries no `frozen` tests and the compiler does not have to unswitch the loop.
 enum : int { M_PLAIN = 0, M_AUTO_RESET = 1, M_FREEZE = 2 };
 
-template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
+// FOLD (auto-reset, K = 1, checked by the host: RolloutArgs::fold_reset): the state reset rides on the np.maximum select -- the
+// stock of a finished episode becomes x_reset = s_reset + 1, whose s = x - 1 is s_reset bit for bit -- instead of a second pair of
+// selects after the step (two FSEL per environment-step less in the kernel behind bench.py's fused.escapement_in_kernel).
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false, bool FOLD = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
                                               uint64_t gid, const SharedTabs& tb, double& reward_out, bool& done_out) {
   constexpr bool auto_reset = MODE == M_AUTO_RESET, freeze = MODE == M_FREEZE;
+  static_assert(!FOLD || (MODE == M_AUTO_RESET && PM == P_KONE), "the folded reset is for auto-reset with K = 1");
   double x = __dadd_rn(e.s, 1.0);
   if (PM != P_KONE) x = __dmul_rn(x, e.K);
   double quota;
@@ -417,11 +421,12 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
     g = __dmul_rn(x1, exp_tab(ex, tb));
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
-  const double x2 = sel64(alive, g, 0.0);
-  const double s2 = __dsub_rn(div_pm<PM>(x2, e.K, kdq), 1.0);
-  const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
   e.years += 1;
   const bool done = (e.years > a.Tmax) || !alive;
+  // FOLD: not done implies alive, so (done ? x_reset : g) is np.maximum's result wherever the episode goes on
+  const double x2 = FOLD ? sel64(done, a.x_reset_fold, g) : sel64(alive, g, 0.0);
+  const double s2 = __dsub_rn(div_pm<PM>(x2, e.K, kdq), 1.0);
+  const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
   reward_out = reward;
   done_out = done;
   e.ret = __dadd_rn(e.ret, reward);
@@ -443,19 +448,19 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
           e.quota_const = policy_quota_msy<PM>(a, e.K, unused);
         }
       }
-      e.s = a.s_reset;
+      if (!FOLD) e.s = a.s_reset;
     } else if (freeze) {
       e.frozen = true;
     }
   }
 }
 
-template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false>
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool SAFE = false, bool FOLD = false>
 __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, double action, double z, int t,
                                               uint64_t gid, const SharedTabs& tb) {
   double reward;
   bool done;
-  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e, action, z, t, gid, tb, reward, done);
+  fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE, FOLD>(a, e, action, z, t, gid, tb, reward, done);
 }
 
 // the return to report: all episodes (auto-reset), or the first one (frozen environments stop accumulating by themselves)
@@ -466,7 +471,7 @@ __device__ __forceinline__ double fast_env_return(const FastEnv& e) {
 
 // TRACE: per-step observation / reward / done rows [T, n] written with streaming stores (the rollout-buffer fill of a
 // whole chunk in one launch).  Not combined with freeze-on-done or an action trace; those go to the generic kernel.
-template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false>
+template <int GROWTH, int PM, int POLICY, bool NOISY, int MODE, bool TRACE = false, bool FOLD = false>
 __global__ void __launch_bounds__(fast_bs(GROWTH), fast_minblocks(GROWTH)) rollout_fast_kernel(const RolloutArgs a) {
   // the Box-Muller tables, staged once per block for the T draws of every thread (normal.cuh)
   constexpr bool TABLES = NOISY || GROWTH == TIPPING;     // Box-Muller tables, and the exp table of the tipping-point growth
@@ -555,8 +560,8 @@ __global__ void __launch_bounds__(fast_bs(GROWTH), fast_minblocks(GROWTH)) rollo
       tr_rew += row_f64;
       tr_done += row_u8;
     } else {
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e0, act.x, z0, t, gid0, tb);
-      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE>(a, e1, act.y, z1, t, gid1, tb);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE, FOLD>(a, e0, act.x, z0, t, gid0, tb);
+      fast_env_step<GROWTH, PM, POLICY, NOISY, MODE, SAFE, FOLD>(a, e1, act.y, z1, t, gid1, tb);
     }
     return false;
   };
@@ -654,6 +659,14 @@ __global__ void __launch_bounds__(128) rollout_sweep_kernel(const RolloutArgs a)
   }
 }
 
+// FISHING_K2_FOLD=0 in the environment: the auto-reset fast path overwrites the state after the step (A/B, tests compare both)
+static bool fold_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FISHING_K2_FOLD");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 static int done_mode(const RolloutArgs& a) {
   return (a.flags & FISHING_AUTO_RESET) ? M_AUTO_RESET : (a.flags & FISHING_FREEZE_DONE) ? M_FREEZE : M_PLAIN;
 }
@@ -668,7 +681,15 @@ static void launch_fast_m(const RolloutArgs& a, int grid, int block, cudaStream_
     return;
   }
   switch (done_mode(a)) {
-    case M_AUTO_RESET: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET><<<grid, block, 0, st>>>(a); break;
+    case M_AUTO_RESET:
+      if constexpr (PM == P_KONE) {
+        if (a.fold_reset && fold_enabled()) {
+          rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET, false, true><<<grid, block, 0, st>>>(a);
+          break;
+        }
+      }
+      rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_AUTO_RESET><<<grid, block, 0, st>>>(a);
+      break;
     case M_FREEZE: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_FREEZE><<<grid, block, 0, st>>>(a); break;
     default: rollout_fast_kernel<GROWTH, PM, POLICY, NOISY, M_PLAIN><<<grid, block, 0, st>>>(a); break;
   }

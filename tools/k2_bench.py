@@ -56,6 +56,7 @@ def main():
                 "ret_hash": int(out["ret"].view(torch.int64).sum())}
 
     res["v1_escapement_sigma0.01"] = fused(nat.V1, "escapement", 0.01, S=0.4996)
+    res["v1_escapement_sigma0.01_autoreset"] = fused(nat.V1, "escapement", 0.01, S=0.4996, auto_reset=True)
     res["v1_escapement_sigma0"] = fused(nat.V1, "escapement", 0.0, S=0.4996)
     res["v2_escapement_sigma0.05_T1000"] = fused(nat.V2, "escapement", 0.05, S=float.fromhex("0x1.9374bcp-1"), Tmax=1000)
     res["v1_K2_escapement_sigma0.01"] = fused(nat.V1, "escapement", 0.01, S=0.9, K=2.0)
