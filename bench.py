@@ -538,12 +538,12 @@ def run_gpu(args):
                 fused[name]["roofline"] = {"unavailable": repr(exc)}
             del b3
 
-        fused_policy_leg(nat.V1, "escapement_in_kernel", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi1ELb0EE",
+        fused_policy_leg(nat.V1, "escapement_in_kernel", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi1ELb0ELb1EE",
                          0.49960005283355713,      # float32 BMSY of the default logistic model (tests/golden/kat.json kat1.S)
                          29, True, False, **CFG)   # fishing-v1 step 22 + continuous escapement policy 6 + return accumulation 1
-        fused_policy_leg(nat.V1, "escapement_in_kernel_plain", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi0ELb0EE",
+        fused_policy_leg(nat.V1, "escapement_in_kernel_plain", "rollout_fast_kernelILi0ELi0ELi1ELb1ELi0ELb0ELb0EE",
                          0.49960005283355713, 29, False, False, **CFG)   # the same without auto-reset (the reference's plain loop)
-        fused_policy_leg(nat.V2, "tipping_escapement_in_kernel", "rollout_fast_kernelILi1ELi0ELi1ELb1ELi2ELb0EE",
+        fused_policy_leg(nat.V2, "tipping_escapement_in_kernel", "rollout_fast_kernelILi1ELi0ELi1ELb1ELi2ELb0ELb0EE",
                          float.fromhex("0x1.9374bcp-1"), 31, False, True, r=0.3, K=1.0, C=0.5, sigma=0.05, x0=0.75, Tmax=1000)
     del obs, rew, done
     torch.cuda.empty_cache()
