@@ -421,12 +421,21 @@ __device__ __forceinline__ void fast_env_step(const RolloutArgs& a, FastEnv& e, 
     g = __dmul_rn(x1, exp_tab(ex, tb));
   }
   const bool alive = (g > 0.0) || (g != g);                      // np.maximum(g, 0): NaN propagates
-  e.years += 1;
-  const bool done = (e.years > a.Tmax) || !alive;
-  // FOLD: not done implies alive, so (done ? x_reset : g) is np.maximum's result wherever the episode goes on
-  const double x2 = FOLD ? sel64(done, a.x_reset_fold, g) : sel64(alive, g, 0.0);
+  bool done = false;
+  double x2;
+  if (FOLD) {   // not done implies alive, so (done ? x_reset : g) is np.maximum's result wherever the episode goes on
+    e.years += 1;
+    done = (e.years > a.Tmax) || !alive;
+    x2 = sel64(done, a.x_reset_fold, g);
+  } else {
+    x2 = sel64(alive, g, 0.0);
+  }
   const double s2 = __dsub_rn(div_pm<PM>(x2, e.K, kdq), 1.0);
   const double reward = (SAFE || (PM == P_UNIFORM && a.kd.odd)) ? py_max(h, 0.0) : h;   // see the comment on FastEnv
+  if (!FOLD) {  // the source order the other instantiations were tuned with (register allocation: tests/test_cpu_host.py)
+    e.years += 1;
+    done = (e.years > a.Tmax) || !alive;
+  }
   reward_out = reward;
   done_out = done;
   e.ret = __dadd_rn(e.ret, reward);
